@@ -1,0 +1,367 @@
+"""Scene flattener: component tree -> the SoA tables of include/optb.h.
+
+Duck-typed: it only reads attributes, so the same function serves optable_b200's own scene
+classes and objects of the reference package (tests feed one scene to both back ends).
+Flatten map = SURVEY.md Appendix D. What is read, and where the reference defines it:
+
+  pose            comp.origin, comp.transform_matrix           optical_component.py:19-20
+  inverse         np.linalg.inv(transform_matrix)              optical_component.py:108
+  lab AABB        comp.bbox (the object's own cached value)    optical_component.py:62-97,
+                                                               component_group.py:28-47
+  group children  comp.components, DFS pre-order               component_group.py:104-115
+  surface         comp.surface (+ class name)                  surfaces.py
+  physics         reflectivity / transmission / focal_length / roc / _n1 / _n2
+  caps            max_interact_count, _interact_count          optical_component.py:37-38,136-149
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi as A
+
+
+class FlattenError(NotImplementedError):
+    """The scene uses a construct the device tables cannot express (no CPU fallback exists)."""
+
+
+def _mro_names(obj):
+    return {k.__name__ for k in type(obj).__mro__}
+
+
+def _closure_map(fn):
+    code = getattr(fn, "__code__", None)
+    cells = getattr(fn, "__closure__", None)
+    if code is None or not cells:
+        return {}
+    return {name: cell.cell_contents for name, cell in zip(code.co_freevars, cells)}
+
+
+class _Materials:
+    def __init__(self):
+        self.kind, self.f, self._index = [], [], {}
+
+    def add(self, m) -> int:
+        key, kind, row = self._describe(m)
+        if key in self._index:
+            return self._index[key]
+        self._index[key] = len(self.kind)
+        self.kind.append(kind)
+        self.f.append(row)
+        return self._index[key]
+
+    @staticmethod
+    def _describe(m):
+        row = [0.0] * A.MF_STRIDE
+        if isinstance(m, (int, float, np.integer, np.floating)):
+            row[0] = float(m)
+            return ("c", row[0]), A.MAT_CONST, row
+        if hasattr(m, "Bs") and hasattr(m, "Cs"):
+            Bs, Cs = [float(b) for b in m.Bs], [float(c) for c in m.Cs]
+            if len(Bs) != 3 or len(Cs) != 3:
+                raise FlattenError("Sellmeier materials need exactly 3 (B, C) pairs")
+            row[0:3], row[3:6] = Bs, Cs
+            return ("s", tuple(Bs), tuple(Cs)), A.MAT_SELLMEIER, row
+        nc = getattr(m, "n_const", None)
+        if nc is None:
+            # reference Material(name, n=<number>) hides the number in a lambda closure (material.py:8-9)
+            cm = _closure_map(getattr(m, "n_func", None))
+            if set(cm) == {"n"} and isinstance(cm["n"], (int, float, np.integer, np.floating)):
+                nc = cm["n"]
+        if nc is None:
+            raise FlattenError(f"material {m!r}: arbitrary n(wavelength) callables are not supported on the device")
+        row[0] = float(nc)
+        return ("c", row[0]), A.MAT_CONST, row
+
+
+def _asphere_spec(surface):
+    spec = getattr(surface, "asphere_spec", None)
+    if spec is None:
+        cm = _closure_map(surface.f_asphere)
+        if set(cm) == {"R", "kappa", "a4", "a6", "a8"}:
+            spec = ("parametric", cm)
+        elif set(cm) == {"EFL", "n"}:
+            spec = ("exact_spherical", cm)
+        else:
+            raise FlattenError("ASphere.f_asphere: only the parametric and exact-spherical profiles are supported")
+    form, p = spec
+    if form == "parametric":
+        return A.ASPH_PARAMETRIC, [float(p["R"]), float(p["kappa"]), float(p["a4"]), float(p["a6"]), float(p["a8"])]
+    if form == "exact_spherical":
+        return A.ASPH_EXACT_SPH, [float(p["EFL"]), float(p["n"]), 0.0, 0.0, 0.0]
+    raise FlattenError(f"unknown asphere form {form!r}")
+
+
+def _csg_spec(surface):
+    spec = getattr(surface, "csg", None)
+    if spec is not None:
+        return spec
+    fn = surface.__dict__.get("within_boundary")
+    cm = _closure_map(fn)
+    if fn is None or set(cm) != {"self", "other"}:
+        raise FlattenError("bare Plane surface has no boundary (surfaces.py:29-33)")
+    op = "subtract" if "subtract" in fn.__qualname__ else "union" if "union" in fn.__qualname__ else None
+    if op is None:
+        raise FlattenError("unrecognised composite plane")
+    return op, cm["self"], cm["other"]
+
+
+class FlatScene:
+    """Numpy tables + bookkeeping for one OpticalTable."""
+
+    def __init__(self, components, monitors=()):
+        self._ni, self._nf, self._aux = [], [], []
+        self._mats = _Materials()
+        self.leaves = []       # leaf index -> component object
+        self.capslots = []     # cap slot -> component object
+        self.max_children = 0  # most rays one interaction can emit (<=1: no splitting anywhere)
+        for c in components:
+            self._visit(c, in_group=False)
+        self.node_i = np.ascontiguousarray(np.array(self._ni, dtype=np.int32).reshape(-1, A.NI_STRIDE))
+        self.node_f = np.ascontiguousarray(np.array(self._nf, dtype=np.float64).reshape(-1, A.NF_STRIDE))
+        self.mat_kind = np.array(self._mats.kind or [0], dtype=np.int32)
+        self.mat_f = np.array(self._mats.f or [[1.0] + [0.0] * (A.MF_STRIDE - 1)], dtype=np.float64)
+        self.aux = np.array(self._aux or [0.0], dtype=np.float64)
+        self.monitors = list(monitors)
+        self.mon_f = np.zeros((max(len(self.monitors), 1), A.MON_STRIDE), dtype=np.float64)
+        for k, m in enumerate(self.monitors):
+            T = np.asarray(m.transform_matrix, dtype=np.float64)
+            self.mon_f[k, A.MON_ORIGIN:A.MON_ORIGIN + 3] = np.asarray(m.origin, dtype=np.float64)
+            self.mon_f[k, A.MON_TINV:A.MON_TINV + 9] = np.linalg.inv(T).reshape(-1)
+            self.mon_f[k, A.MON_HW] = m.width / 2
+            self.mon_f[k, A.MON_HH] = m.height / 2
+            self.mon_f[k, A.MON_TY:A.MON_TY + 3] = T @ np.array([0.0, 1.0, 0.0])
+            self.mon_f[k, A.MON_TZ:A.MON_TZ + 3] = T @ np.array([0.0, 0.0, 1.0])
+        self.n_nodes = self.node_i.shape[0]
+        self.n_leaves = len(self.leaves)
+        self.n_materials = len(self._mats.kind)
+        self.n_monitors = len(self.monitors)
+        self.n_capslots = len(self.capslots)
+
+    # -- tree walk ---------------------------------------------------------------------------
+    def _new_node(self):
+        self._ni.append([0] * A.NI_STRIDE)
+        self._nf.append([0.0] * A.NF_STRIDE)
+        ni = self._ni[-1]
+        ni[A.NI_CAPSLOT] = -1
+        ni[A.NI_LEAF] = -1
+        return len(self._ni) - 1
+
+    def _visit(self, comp, in_group):
+        if hasattr(comp, "components") and "ComponentGroup" in _mro_names(comp):
+            if len(comp.components) == 0:
+                return  # nothing to hit (the reference would raise in merge_bboxs on first use)
+            idx = self._new_node()
+            ni, nf = self._ni[idx], self._nf[idx]
+            ni[A.NI_GEOM] = A.G_GROUP
+            ni[A.NI_AABB] = 1
+            nf[A.NF_AABB:A.NF_AABB + 6] = [float(v) for v in comp.bbox]
+            for child in comp.components:
+                self._visit(child, in_group=True)
+            ni[A.NI_SKIP] = len(self._ni)
+            return
+        names = _mro_names(comp)
+        sname = type(comp.surface).__name__
+        if "PointObj" in names or sname == "Point":
+            return  # Point.f = |P| never changes sign -> never hit (surfaces.py:68-86)
+        if "Monitor" in names:
+            raise FlattenError("a Monitor inside table.components is a pass-through that re-hits itself; unsupported")
+        idx = self._new_node()
+        ni, nf = self._ni[idx], self._nf[idx]
+        ni[A.NI_SKIP] = idx + 1
+        ni[A.NI_AABB] = 1 if in_group else 0
+        ni[A.NI_LEAF] = len(self.leaves)
+        self.leaves.append(comp)
+        T = np.asarray(comp.transform_matrix, dtype=np.float64)
+        nf[A.NF_ORIGIN:A.NF_ORIGIN + 3] = [float(v) for v in comp.origin]
+        nf[A.NF_TINV:A.NF_TINV + 9] = np.linalg.inv(T).reshape(-1).tolist()
+        nf[A.NF_T:A.NF_T + 9] = T.reshape(-1).tolist()
+        if in_group:
+            nf[A.NF_AABB:A.NF_AABB + 6] = [float(v) for v in comp.bbox]
+        self._geometry(comp.surface, sname, ni, nf)
+        self._physics(comp, names, ni, nf)
+        cap = getattr(comp, "max_interact_count", None)
+        if cap is not None:
+            ni[A.NI_CAPSLOT] = len(self.capslots)
+            nf[A.NF_CAPMAX] = float(cap)
+            self.capslots.append(comp)
+
+    def _poly_record(self, s):
+        off = len(self._aux)
+        v2 = np.asarray(s._verts2d, dtype=np.float64)
+        u, v = s._basis
+        rec = [float(len(v2))] + [float(x) for x in s._normal] + [float(x) for x in s.vertices[0]]
+        rec += [float(x) for x in u] + [float(x) for x in v] + [float(x) for x in s._bbox]
+        assert len(rec) == A.POLY_HEADER
+        self._aux.extend(rec + v2.reshape(-1).tolist())
+        return off
+
+    def _planar_shape(self, s):
+        """(kind, p0, p1) of a simple planar shape (also used as CSG operand)."""
+        n = type(s).__name__
+        if n == "Circle":
+            return A.G_CIRCLE, float(s.radius), 0.0
+        if n == "Rectangle":
+            return A.G_RECT, s.width / 2, s.height / 2
+        if n == "Polygon" and s.planar:
+            return A.G_POLY2D, float(self._poly_record(s)), 0.0
+        raise FlattenError(f"surface {n} cannot be used as a planar aperture operand")
+
+    def _geometry(self, s, sname, ni, nf):
+        p = [0.0] * 8
+        if sname == "Circle":
+            ni[A.NI_GEOM], p[0] = A.G_CIRCLE, float(s.radius)
+        elif sname == "Rectangle":
+            ni[A.NI_GEOM] = A.G_RECT
+            p[0], p[1] = s.width / 2, s.height / 2
+        elif sname == "Sphere":
+            ni[A.NI_GEOM] = A.G_SPHERE
+            p[0], p[1] = float(s.radius), float(s.height)
+            p[2:8] = [float(v) for v in s.get_bbox_local()]
+        elif sname == "ASphere":
+            ni[A.NI_GEOM] = A.G_ASPHERE
+            form, coeffs = _asphere_spec(s)
+            ni[A.NI_AUX] = form
+            p[0] = float(s.radius)
+            p[1:6] = coeffs
+            p[6], p[7] = float(s.xmin), float(s.xmax)
+        elif sname == "Cylinder":
+            ni[A.NI_GEOM] = A.G_CYL
+            p[0], p[1] = float(s.radius), float(s.height)
+            p[2], p[3] = float(s.theta_range[0]), float(s.theta_range[1])
+        elif sname == "Polygon":
+            ni[A.NI_GEOM] = A.G_POLY2D if s.planar else A.G_POLY3D
+            ni[A.NI_AUX] = self._poly_record(s)
+        elif sname == "Plane":
+            op, sa, sb = _csg_spec(s)
+            ni[A.NI_GEOM] = A.G_CSG
+            p[0] = 0.0 if op == "subtract" else 1.0
+            p[1], p[2], p[3] = self._planar_shape(sa)
+            p[4], p[5], p[6] = self._planar_shape(sb)
+        else:
+            raise FlattenError(f"unsupported surface class {sname}")
+        nf[A.NF_P:A.NF_P + 8] = p
+
+    def _physics(self, comp, names, ni, nf):
+        if "BaseMirror" in names:
+            ni[A.NI_INTER] = A.I_MIRROR
+            nf[A.NF_REFL], nf[A.NF_TRANS] = float(comp.reflectivity), float(comp.transmission)
+            nchild = int(comp.reflectivity > 0) + int(comp.transmission > 0)
+        elif "BaseRefraciveSurface" in names:
+            ni[A.NI_INTER] = A.I_REFRACT
+            nf[A.NF_REFL], nf[A.NF_TRANS] = float(comp.reflectivity), float(comp.transmission)
+            d = vars(comp)
+            ni[A.NI_MAT1] = self._mats.add(d["_n1"])
+            ni[A.NI_MAT2] = self._mats.add(d["_n2"])
+            roc = getattr(comp, "roc", math.inf)
+            if callable(roc):
+                if ni[A.NI_GEOM] != A.G_ASPHERE:
+                    raise FlattenError("callable roc is only supported for ASphere surfaces")
+                ni[A.NI_ROCKIND] = A.ROC_ASPHERE_FD
+            elif math.isinf(float(roc)) and float(roc) > 0:
+                ni[A.NI_ROCKIND] = A.ROC_INF
+                nf[A.NF_ROC] = math.inf
+            else:
+                ni[A.NI_ROCKIND] = A.ROC_CONST
+                nf[A.NF_ROC] = float(roc)
+            nchild = 2 if comp.reflectivity > 0 else 1
+        elif "Lens" in names:
+            ni[A.NI_INTER] = A.I_THINLENS
+            nf[A.NF_FOCAL], nf[A.NF_TRANS] = float(comp.focal_length), float(comp.transmission)
+            nchild = 1
+        elif "Block" in names:
+            ni[A.NI_INTER] = A.I_ABSORB
+            nchild = 0
+        else:
+            raise FlattenError(f"component class {type(comp).__name__} has no device interaction")
+        self.max_children = max(self.max_children, nchild)
+
+    # -- ABI view ----------------------------------------------------------------------------
+    def desc(self) -> A.SceneDesc:
+        d = A.SceneDesc()
+        d.abi_version = A.ABI_VERSION
+        d.n_nodes, d.n_leaves = self.n_nodes, self.n_leaves
+        d.n_materials, d.n_monitors, d.n_capslots = self.n_materials, self.n_monitors, self.n_capslots
+        d.n_aux = self.aux.size
+        d.node_i = self.node_i.ctypes.data
+        d.node_f = self.node_f.ctypes.data
+        d.mat_kind = self.mat_kind.ctypes.data
+        d.mat_f = self.mat_f.ctypes.data
+        d.mon_f = self.mon_f.ctypes.data
+        d.aux = self.aux.ctypes.data
+        d._keepalive = self  # arrays must outlive the struct
+        return d
+
+
+def material_value(m, wavelength_m: float = 0.0) -> float:
+    """Index of a Material-like object or a plain number at a wavelength in metres."""
+    if isinstance(m, (int, float, np.integer, np.floating)):
+        return float(m)
+    return float(m.n(wavelength_m))
+
+
+def pack_rays(rays):
+    """list[Ray] -> dict of SoA numpy arrays (include/optb.h optb_rays), family table, unit.
+
+    Reads the fields Ray.__init__ sets (ray.py:63-105): origin, _direction, intensity, wavelength,
+    length (None -> +inf), alive, qo (None -> flag), _pathlength, n, _id, unit.
+    """
+    n = len(rays)
+    out = {k: np.empty(n, dtype=np.float64) for k in A.RAY_F64}
+    flags = np.zeros(n, dtype=np.uint32)
+    family = np.zeros(n, dtype=np.int32)
+    fam_index, fam_ids = {}, []
+    units = set()
+    for i, r in enumerate(rays):
+        o, d = r.origin, r._direction
+        out["ox"][i], out["oy"][i], out["oz"][i] = o[0], o[1], o[2]
+        out["dx"][i], out["dy"][i], out["dz"][i] = d[0], d[1], d[2]
+        out["intensity"][i] = r.intensity
+        out["wavelength"][i] = r.wavelength if r.wavelength is not None else 0.0
+        q = r.qo
+        f = 0
+        if q is not None:
+            out["q_re"][i], out["q_im"][i] = q.real, q.imag
+            f |= A.RF_HASQ
+        else:
+            out["q_re"][i] = out["q_im"][i] = 0.0
+        if r.alive:
+            f |= A.RF_ALIVE
+        flags[i] = f
+        out["pathlength"][i] = r._pathlength
+        out["n_medium"][i] = r.n
+        out["length"][i] = math.inf if r.length is None else r.length
+        rid = r._id
+        if rid not in fam_index:
+            fam_index[rid] = len(fam_ids)
+            fam_ids.append(rid)
+        family[i] = fam_index[rid]
+        units.add(float(r.unit))
+    if len(units) > 1:
+        raise FlattenError("rays with different .unit in one batch are not supported")
+    out["flags"], out["family"] = flags, family
+    return out, fam_ids, (units.pop() if units else 1e-2)
+
+
+def rays_struct(arrs, n=None) -> A.Rays:
+    """ctypes view over a dict of numpy arrays (host pointers)."""
+    s = A.Rays()
+    s.n = int(n if n is not None else len(arrs["ox"]))
+    for k in A.RAY_F64:
+        a = arrs.get(k)
+        setattr(s, k, None if a is None else a.ctypes.data)
+    for k in ("flags", "family"):
+        a = arrs.get(k)
+        setattr(s, k, None if a is None else a.ctypes.data)
+    s._keepalive = arrs
+    return s
+
+
+def trace_cap(perfomance_limit) -> int:
+    """MAX_TRACE_NUM semantics (optical_table.py:86-97): loop runs while trace_num < MAX."""
+    cap = 2000
+    if perfomance_limit is not None and "max_trace_num" in perfomance_limit:
+        cap = perfomance_limit["max_trace_num"]
+    return max(0, int(math.ceil(cap)))

@@ -1,0 +1,240 @@
+"""Scene fixtures shared by the parity tests, the golden-vector generator and the benchmarks.
+
+Every builder takes a namespace `ns` exposing the optable public names (Ray, Mirror, Lens, ...): the
+reference package in the build container, optable_b200 everywhere. The geometry restates the
+reference's example scripts (examples/*.py, cited per builder) and SURVEY.md section 8(d).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SEED = 20261018
+
+
+class Scene:
+    def __init__(self, components, rays, monitors=(), limit=None):
+        self.components, self.rays, self.monitors, self.limit = list(components), list(rays), list(monitors), limit
+
+
+def gaussian_beam(ns):
+    """C1: examples/gaussian_beam.py:16-44 (README scene)."""
+    wl, w0 = 780e-9, 10e-6
+    rays = [ns.Ray([-10, y, 0], [1, 0, 0], wavelength=wl, w0=w0) for y in (0, 2, 4, 6, 9)]
+    rays.append(ns.Ray([-10, 21, 0], [1, 0, 0], wavelength=wl, w0=w0).RotZ(-np.pi / 4))
+    comps = [
+        ns.Mirror([0, 0, 0]).RotZ(np.pi / 6),
+        ns.Lens([0, 2, 0], radius=0.8, focal_length=5),
+        ns.Lens([0, 4, 0], radius=0.8, focal_length=10),
+        ns.Lens([0, 6.5, 0], radius=0.8, focal_length=10),
+        ns.GlassSlab([0, 9, 0], n1=1, n2=2, thickness=5),
+        ns.Mirror([0, 11, 0]).RotZ(-np.pi / 2),
+    ]
+    return Scene(comps, rays)
+
+
+def glass_slab(ns):
+    """examples/glass_slab.py:34-52: splitting at both faces; the 2000-pop cap binds."""
+    rays = [ns.Ray([-3, 2, 0], [np.cos(np.pi / 6), -np.sin(np.pi / 6), 0], wavelength=780e-7, w0=2e-4).Propagate(-2)]
+    gs = ns.GlassSlab([0, 0, 0], width=2, height=2, thickness=0.5, n1=1, n2=1.5, reflectivity=0.2)
+    return Scene([gs], rays, limit={"max_trace_num": 300})
+
+
+def chromatic(ns):
+    """examples/chromatic_aberration.py:16-40: 3 wavelengths share one _id; Sellmeier glass."""
+    r0 = [ns.Ray([-3, 2, 0], [np.cos(np.pi / 6), -np.sin(np.pi / 6), 0], wavelength=780e-7, w0=20e-4).Propagate(-2)]
+    rays = ns.multiplex_rays_in_wavelength(r0, [780e-7, 560e-7, 400e-7])
+    gs = ns.GlassSlab([0, 0, 0], width=2, height=2, thickness=0.5, n1=ns.Vacuum(), n2=ns.Glass_NBK7(), reflectivity=0.2)
+    return Scene([gs], rays, limit={"max_trace_num": 200})
+
+
+def cavity(ns, dt1=0.02, dt2=0.02, gaussian=False, n_rays=1, limit=None):
+    """examples/cavity_4mir.py:17-40 (misaligned: escapes after 21 bounces; aligned: runs to the cap)."""
+    L, D, R = 10 * 4 / 3, 4, 0.9
+    comps = [
+        ns.Mirror([0, 0, 0], radius=D, reflectivity=R).RotZ(-np.pi / 4),
+        ns.Mirror([L, 0, 0], radius=D, reflectivity=R).RotZ(+np.pi / 4 + dt1),
+        ns.Mirror([L, -L, 0], radius=D, reflectivity=R).RotZ(-np.pi / 4 + dt2),
+        ns.Mirror([0, -L, 0], radius=D, reflectivity=R).RotZ(+np.pi / 4),
+    ]
+    rng = np.random.default_rng(SEED)
+    rays = []
+    for i in range(n_rays):
+        kw = dict(wavelength=780e-7, w0=61e-4) if gaussian else {}
+        if i == 0:
+            rays.append(ns.Ray([2, 0, 0], [1, 0, 0], **kw))
+        else:
+            y, z = rng.uniform(-1, 1, 2)
+            ty, tz = rng.uniform(-2e-5, 2e-5, 2)
+            rays.append(ns.Ray([2, y, z], [1, ty, tz], **kw))
+    return Scene(comps, rays, limit=limit)
+
+
+def cavity_aligned(ns):
+    return cavity(ns, 0.0, 0.0, gaussian=True, n_rays=3, limit={"max_trace_num": 400})
+
+
+def doublet(ns, n_rays=6):
+    """Edmund #88-597 doublet (examples/calibrate_4f.py:126-147) + monitor, 3 wavelengths."""
+    lens = ns.Doublet([30.3964, 0, 0], CT1=1.359, CT2=0.6, R1=18.405, R2=-13.734, R3=-39.933,
+                      n12=ns.Glass_NBK7(), n23=ns.Glass_NSF5(), diameter=7.5)
+    mon = ns.Monitor([62, 0, 0], 10, 10)
+    rng = np.random.default_rng(SEED + 1)
+    r0 = [ns.Ray([0, 2, -1], [1, 0, 0], wavelength=780e-7, w0=61e-4)]
+    for _ in range(n_rays - 1):
+        y, z = rng.uniform(-3, 3, 2)
+        r0.append(ns.Ray([0, y, z], [1, 0.01 * rng.standard_normal(), 0.01 * rng.standard_normal()],
+                         wavelength=780e-7, w0=61e-4))
+    rays = ns.multiplex_rays_in_wavelength(r0, [780e-7, 560e-7, 400e-7])
+    return Scene([lens], rays, [mon])
+
+
+def asphere_lens9(ns, origin):
+    """examples/calibrate_4f.py:149-180 (LENS == 9)."""
+    EFL, CT = 43.17, 0.8
+    n = ns.Glass_UVFS()
+    R = EFL * (n.n(780e-9) - 1)
+    return ns.ASphericParametricLens(origin, CT=CT, diameter=2.54 * 3, R=R, n=n, kappa=-1.03113,
+                                     a4=-0.00223 * (1e-3 / 1e-2) ** 4, a6=0.006353 * (1e-3 / 1e-2) ** 6, name="L0")
+
+
+def telescope_4f(ns, n_rays=7, disc=True):
+    """C2: two LENS-9 aspheres as a 4f relay with monitors at x=0 and x=2F1+2F2
+    (optical_table.py:328-336 geometry)."""
+    F1 = F2 = 43.17
+    l0 = asphere_lens9(ns, [F1, 0, 0])
+    l1 = asphere_lens9(ns, [F1 + 2 * F2, 0, 0]).RotZ(np.pi)
+    mon0 = ns.Monitor([0, 0, 0], width=5, height=5)
+    mon1 = ns.Monitor([2 * F1 + 2 * F2, 0, 0], width=5, height=5)
+    rng = np.random.default_rng(SEED + 2)
+    rays = []
+    for i in range(n_rays):
+        if disc:
+            rr, th = 3.0 * np.sqrt(rng.uniform()), rng.uniform(0, 2 * np.pi)
+            y, z = rr * np.cos(th), rr * np.sin(th)
+        else:
+            y, z = (i - n_rays // 2) * 0.6, 0.0
+        rays.append(ns.Ray([-10, y, z], [1, 0, 0], wavelength=780e-7, w0=61e-4))
+    return Scene([l0, l1], rays, [mon0, mon1])
+
+
+def exact_asphere(ns):
+    """ASphericExactSphericalLens (component_group.py:1065-1082) with tilted rays."""
+    lens = ns.ASphericExactSphericalLens([10, 0, 0], EFL=20.0, CT=0.6, diameter=5.0, n=1.5)
+    mon = ns.Monitor([30, 0, 0], 6, 6)
+    rng = np.random.default_rng(SEED + 3)
+    rays = [ns.Ray([0, *rng.uniform(-2, 2, 2)], [1, *(0.02 * rng.standard_normal(2))], wavelength=633e-7, w0=50e-4)
+            for _ in range(8)]
+    return Scene([lens], rays, [mon])
+
+
+def mirror_pair(ns):
+    """examples/mirror_pair.py:20-36."""
+    r0 = ns.Ray([-10, 1, 0], [1, 0, 0])._RotAround([0, 1, 0], [0, 0, 0], 0.1)
+    mp = ns.MirrorPair([3, 0, 0], 4, 4).RotX(0.3)
+    return Scene([mp], [r0], [ns.Monitor([1, 0, 0], 5, 5), ns.Monitor([-3, 0, 0], 5, 5)])
+
+
+def prism_refl(ns):
+    """examples/prism_refl.py:21-65: TriangularPrism with interact caps and explicit ray ids."""
+    theta, L, wl, w0 = 0.00956, 6, 780e-7, 61e-4
+    n = ns.Glass_NBK7().n(780e-9)
+    D = 3 - 210e-4
+    rays = [ns.Ray([3, y + L / 2, 0], [-1, 0, 0], wavelength=wl, w0=w0, id=i).Propagate(-3).RotZ(theta)
+            for i, y in enumerate(np.linspace(-D, D, 5))]
+    ps = ns.TriangularPrism(origin=[0, 0, 0], width=L, height=L, n1=1, n2=n, alpha=np.pi / 4, beta=np.pi / 2,
+                            reflectivity_1=1, reflectivity_3=0.01, max_interact_count_2=10, max_interact_count_3=10)
+    return Scene([ps], rays, [ns.Monitor([-3, 0, 0], width=L, height=L)], limit={"max_trace_num": 300})
+
+
+def dove_prism(ns):
+    """examples/dove_prism.py:31-66: 2-D and 3-D polygon faces, TIR on the base."""
+    L, D, Ng = 6.34, 1.515, 1.515
+    dp = ns.DovePrism([0, 0, 0], L=L, D=D, Ng=Ng)
+    z0 = dp.z0
+    rays = [ns.Ray([x, -50, z0], [0, 1, 0]) for x in np.linspace(-0.6, 0.6, 7)]
+    rays += [ns.Ray([x, 3, z], [0, -1, 0]) for x in np.linspace(-1, 1, 3) for z in np.linspace(-1, 1, 3)]
+    rays += [ns.Ray([3, y, z + 1], [-1, 0, -0.3]) for y in np.linspace(-1, 1, 3) for z in np.linspace(-1, 1, 3)]
+    dp = dp.RotX(0.02).RotZ(-0.01).TX(0.1).TZ(0.05).RotYAroundLocal([0, 0, D / 2], theta=0.3)
+    mon0 = ns.Monitor([0, 10, z0], width=2 * D, height=2 * D).RotZ(np.pi / 2)
+    return Scene([dp], rays, [mon0])
+
+
+def gaussian_telescope(ns):
+    """examples/gaussian_telescope.py:20-49 (thin lenses; `diameter=` kwarg is ignored by Lens)."""
+    F, M, D = 5, 5, 2
+    F0, F1, F2, F3 = F, F / M, F * M, F
+    l0 = ns.Lens([F0, 0, 0], focal_length=F0, diameter=D)
+    l2 = ns.Lens([2 * F0 + 2 * F1 + F2, 0, 0], focal_length=F2, diameter=D)
+    l3 = ns.Lens([2 * F0 + 2 * F1 + 2 * F2 + F3, 0, 0], focal_length=F3, diameter=D)
+    mon0 = ns.Monitor([2 * F0 + 2 * F1 + 2 * F2 + 2 * F3, 0, 0], width=D, height=D)
+    rays = [ns.Ray([0, 0.1 * k, 0.05 * k], [1, 0, 0], wavelength=780e-7, w0=61e-4) for k in range(4)]
+    return Scene([l0, l2, l3], rays, [mon0])
+
+
+def misc_components(ns):
+    """Beam splitter, block with a circular hole, cylindrical mirror, wedge, plano-convex, bi-convex, MLA, DMD,
+    MirrorCube, Prism, CircleGlassSlab, finite-length and dead input rays."""
+    comps = [
+        ns.BeamSplitter([2, 0, 0], width=2, height=2, eta=0.3).RotZ(np.pi / 4),
+        ns.Block([6, 0, 0], hole=ns.Circle(0.5), width=3, height=3),
+        ns.CylMirror([12, 0.2, 0], radius=2.0, height=3.0, theta_range=(-np.pi / 3, np.pi / 3)),
+        ns.WedgePlate([2, 5, 0], width=2, height=2, thickness=0.4, wedge_angle=0.05, n1=1.0, n2=1.45),
+        ns.PlanoConvexLens([2, 9, 0], EFL=10.0, CT=0.5, diameter=2.0, R=5.0),
+        ns.BiConvexLens([8, 9, 0], CT=0.6, R1=12.0, R2=-12.0, diameter=2.0, n=1.5),
+        ns.MLA([14, 9, 0], N=(3, 2), pitch=0.5, focal_length=4.0, radius=0.25),
+        ns.DMD([2, -5, 0], N=(2, 2), pitch=0.6, tilt_angle=np.pi / 4 + 0.1),
+        ns.MirrorCube([8, -6, 0], L=2.0),
+        ns.Prism([5, -12, 0], width=2, height=2, n1=1.0, n2=1.5, reflectivity_hyp=0.1),
+        ns.CircleGlassSlab([2, 14, 0], radius=1.0, thickness=0.3, n1=1.0, n2=1.6, reflectivity2=0.05),
+        ns.SquareMirror([20, 0, 0], width=30, height=30, reflectivity=0.5, transmission=0.5),
+    ]
+    rng = np.random.default_rng(SEED + 4)
+    rays = []
+    for y0 in (0.0, 5.0, 9.0, -5.0, -6.0, -12.0, 14.0):
+        for _ in range(4):
+            dy, dz = rng.uniform(-0.3, 0.3, 2)
+            rays.append(ns.Ray([-3, y0 + dy, dz], [1, 0.03 * rng.standard_normal(), 0.03 * rng.standard_normal()],
+                               wavelength=633e-7, w0=30e-4))
+    rays.append(ns.Ray([-3, 0.1, 0], [1, 0, 0], length=4.0))           # limit before the block
+    rays.append(ns.Ray([-3, 0.2, 0], [1, 0, 0], length=7.0, wavelength=500e-7))
+    rays.append(ns.Ray([-3, 0.3, 0], [1, 0, 0], alive=False))
+    rays.append(ns.Ray([-3, 0.9, 0.0], [1, 0, 0]))                      # no q, no wavelength
+    mons = [ns.Monitor([18, 0, 0], 40, 40), ns.Monitor([-2, 0, 0], 40, 40).RotZ(0.2)]
+    return Scene(comps, rays, mons, limit={"max_trace_num": 60})
+
+
+def mma_small(ns):
+    """A small MMA cavity in the style of examples/ripa_gen2_lensless.py:176-200 (nested groups)."""
+    pitch, roc = 420e-4, 2.2
+    m0 = ns.MMA(origin=[-0.1, 0, 0], N=(6, 1), pitch=pitch, roc=roc, n=1.5, thickness=0.1, reflectivity=0.9999,
+                transmission=0, back_transmission=0, back_reflectivity=1)
+    m1 = ns.MMA(origin=[2.0, 0, 0], N=(6, 3), pitch=pitch, roc=roc, n=1.5, thickness=0.1, reflectivity=0.98,
+                transmission=0.3, shifty_z=-0.002).TY(0.01)
+    grp = ns.ComponentGroup([0, 0, 0])
+    grp.add_components([m0, m1])
+    mon = ns.Monitor([2.0 - 1e-4, 0, 0], width=1, height=1)
+    rng = np.random.default_rng(SEED + 5)
+    rays = []
+    for _ in range(6):
+        y, z = rng.uniform(-0.1, 0.1, 2)
+        rays.append(ns.Ray([0, y, z], [1, 0.02 * rng.standard_normal(), 0.02 * rng.standard_normal()],
+                           wavelength=780e-7, w0=40e-4))
+    return Scene([grp], rays, [mon], limit={"max_trace_num": 120})
+
+
+REGISTRY = {
+    "gaussian_beam": gaussian_beam,
+    "glass_slab": glass_slab,
+    "chromatic": chromatic,
+    "cavity_misaligned": cavity,
+    "cavity_aligned": cavity_aligned,
+    "doublet": doublet,
+    "telescope_4f": telescope_4f,
+    "exact_asphere": exact_asphere,
+    "mirror_pair": mirror_pair,
+    "prism_refl": prism_refl,
+    "dove_prism": dove_prism,
+    "gaussian_telescope": gaussian_telescope,
+    "misc_components": misc_components,
+    "mma_small": mma_small,
+}
