@@ -1,0 +1,260 @@
+"""ctypes binding of the C-ABI CUDA library (include/optb.h) + the device-side trace driver.
+
+PyTorch is plumbing here: it owns device memory (tensors whose data_ptr() goes through the ABI) and the
+CUDA stream. All arithmetic of the bounce loop is in optable_b200/liboptb.so. There is no CPU fallback:
+if the extension is missing or no CUDA device is present, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+from .flatten import FlatScene
+
+_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboptb.so")
+_lib = None
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load liboptb.so (built in-tree by optable_b200.build). Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise BackendError(f"{_SO} not found: build it with `python -m optable_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(_SO)
+        L.optb_abi_version.restype = C.c_int
+        L.optb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.optb_ctx_destroy.argtypes = [C.c_void_p]
+        L.optb_last_error.restype = C.c_char_p
+        L.optb_last_error.argtypes = [C.c_void_p]
+        L.optb_scene_upload.argtypes = [C.c_void_p, C.POINTER(A.SceneDesc), C.POINTER(C.c_void_p)]
+        L.optb_scene_destroy.argtypes = [C.c_void_p, C.c_void_p]
+        L.optb_workspace_bytes.restype = C.c_int64
+        L.optb_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        L.optb_trace.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.Rays), C.POINTER(A.Params), C.POINTER(A.Result),
+                                 C.c_void_p, C.c_int64, C.c_void_p]
+        L.optb_trace_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.Rays), C.POINTER(A.Params), C.POINTER(A.Result)]
+        L.optb_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        if L.optb_abi_version() != A.ABI_VERSION:
+            raise BackendError("liboptb.so ABI version does not match optable_b200._abi")
+        _lib = L
+    return _lib
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise BackendError("no CUDA device: optable_b200 has no CPU fallback")
+    return torch
+
+
+_RESULT_DTYPES = None
+
+
+def _result_fields(torch):
+    global _RESULT_DTYPES
+    if _RESULT_DTYPES is None:
+        d = {}
+        for k in A.SEG_F64 + A.HIT_F64:
+            d[k] = torch.float64
+        for k in A.SEG_U32 + A.HIT_U32:
+            d[k] = torch.int32  # bit pattern of uint32; viewed as uint32 on the host
+        for k in A.SEG_I32 + A.HIT_I32:
+            d[k] = torch.int32
+        _RESULT_DTYPES = d
+    return _RESULT_DTYPES
+
+
+class Scene:
+    """Device-resident scene tables (optb_scene handle)."""
+
+    def __init__(self, engine, flat: FlatScene):
+        self.engine, self.flat = engine, flat
+        h = C.c_void_p()
+        desc = flat.desc()
+        engine._check(lib().optb_scene_upload(engine._ctx, C.byref(desc), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib().optb_scene_destroy(self.engine._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One context per CUDA device (optb_ctx)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, device=None):
+        torch = _torch()
+        dev = torch.cuda.current_device() if device is None else int(device)
+        if dev not in cls._cache:
+            cls._cache[dev] = cls(dev)
+        return cls._cache[dev]
+
+    def __init__(self, device=0):
+        self.torch = _torch()
+        self.device = int(device)
+        self._ctx = C.c_void_p()
+        rc = lib().optb_ctx_create(self.device, C.byref(self._ctx))
+        if rc != 0:
+            raise BackendError(f"optb_ctx_create({device}) failed: {rc}")
+        self._workspace = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BackendError(f"liboptb error {rc}: {lib().optb_last_error(self._ctx).decode()}")
+
+    def upload(self, flat: FlatScene) -> Scene:
+        return Scene(self, flat)
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double(0)
+        self._check(lib().optb_measure_fp64_peak(self._ctx, C.byref(v)))
+        return v.value
+
+    # -- device buffers --------------------------------------------------------------------------
+    def _ws(self, nbytes):
+        torch = self.torch
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._workspace
+
+    def rays_to_device(self, arrs):
+        """dict of numpy arrays (flatten.pack_rays) -> dict of CUDA tensors."""
+        torch = self.torch
+        dev = f"cuda:{self.device}"
+        out = {}
+        for k in A.RAY_F64:
+            out[k] = torch.from_numpy(np.ascontiguousarray(arrs[k], dtype=np.float64)).to(dev)
+        out["flags"] = torch.from_numpy(np.ascontiguousarray(arrs["flags"]).view(np.int32)).to(dev)
+        out["family"] = torch.from_numpy(np.ascontiguousarray(arrs["family"], dtype=np.int32)).to(dev)
+        return out
+
+    @staticmethod
+    def _rays_struct(t, n=None):
+        s = A.Rays()
+        s.n = int(t["ox"].numel() if n is None else n)
+        for k in A.RAY_F64:
+            v = t.get(k)
+            setattr(s, k, None if v is None else v.data_ptr())
+        for k in ("flags", "family"):
+            v = t.get(k)
+            setattr(s, k, None if v is None else v.data_ptr())
+        return s
+
+    def alloc_result(self, scene: Scene, seg_capacity, hit_capacity, n_families, cap_counts=None):
+        torch = self.torch
+        dev = f"cuda:{self.device}"
+        dt = _result_fields(torch)
+        t = {}
+        for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32:
+            t[k] = torch.empty(int(seg_capacity), dtype=dt[k], device=dev)
+        for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64:
+            t[k] = torch.empty(int(hit_capacity), dtype=dt[k], device=dev)
+        nm = max(scene.flat.n_monitors, 1)
+        t["hist_y"] = torch.zeros((nm, A.HIST_BINS), dtype=torch.int64, device=dev)
+        t["hist_yz"] = torch.zeros((nm, A.HIST_BINS, A.HIST_BINS), dtype=torch.int64, device=dev)
+        if cap_counts is None:
+            t["cap_counts"] = torch.zeros((max(scene.flat.n_capslots, 1), max(int(n_families), 1)), dtype=torch.int32, device=dev)
+        else:
+            t["cap_counts"] = torch.from_numpy(np.ascontiguousarray(cap_counts, dtype=np.int32)).to(dev)
+        t["counters"] = torch.zeros(A.C_COUNT, dtype=torch.int64, device=dev)
+        r = A.Result()
+        r.seg_capacity, r.hit_capacity = int(seg_capacity), int(hit_capacity)
+        for k, v in t.items():
+            setattr(r, k, v.data_ptr())
+        return r, t
+
+    @staticmethod
+    def make_params(max_trace_num=2000, unit=1e-2, record_segments=True, record_hits=True, record_hist=False,
+                    chain_len=0, n_families=1):
+        p = A.Params()
+        p.max_trace_num, p.unit = int(max_trace_num), float(unit)
+        p.record_segments, p.record_hits, p.record_hist = int(record_segments), int(record_hits), int(record_hist)
+        p.chain_len, p.n_families = int(chain_len), int(n_families)
+        return p
+
+    def trace_device(self, scene: Scene, rays_t, params: A.Params, result: A.Result, max_live=None, stream=None):
+        """Enqueue optb_trace on tensors already resident on the device. Asynchronous for scenes that cannot
+        split rays; returns after the last generation otherwise."""
+        torch = self.torch
+        n = int(rays_t["ox"].numel())
+        splitting = scene.flat.max_children > 1 or params.chain_len > 0
+        live = 0 if not splitting else int(max_live if max_live is not None else max(4 * n, 1024))
+        nbytes = lib().optb_workspace_bytes(scene._h, n, live)
+        ws = self._ws(nbytes)
+        rs = self._rays_struct(rays_t)
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._check(lib().optb_trace(self._ctx, scene._h, C.byref(rs), C.byref(params), C.byref(result),
+                                     ws.data_ptr(), int(ws.numel()), C.c_void_p(st)))
+
+    def trace_host(self, scene: Scene, rays_struct: A.Rays, params: A.Params, result: A.Result):
+        """optb_trace_host: host buffers in, host buffers out (copies inside the call)."""
+        self._check(lib().optb_trace_host(self._ctx, scene._h, C.byref(rays_struct), C.byref(params), C.byref(result)))
+
+    # -- convenience: exact-size traced result on the host, in reference order -------------------------
+    def trace_arrays(self, scene: Scene, arrs, max_trace_num=2000, unit=1e-2, record_segments=True, record_hits=True,
+                     record_hist=False, n_families=None, cap_counts=None, chain_len=0, max_live=None):
+        """Trace a packed ray batch and return numpy result arrays trimmed and sorted to reference order
+        (segments by (root, pop); monitor rows by (root, monitor, pop))."""
+        torch = self.torch
+        n = len(arrs["ox"])
+        if n_families is None:
+            n_families = int(arrs["family"].max()) + 1 if n else 1
+        rays_t = self.rays_to_device(arrs)
+        flat = scene.flat
+        caps0 = None
+        if flat.n_capslots:
+            caps0 = np.zeros((flat.n_capslots, n_families), np.int32) if cap_counts is None else np.array(cap_counts, np.int32)
+        # pass 1: count rows (interact-count side effects go to a scratch table)
+        prm = self.make_params(max_trace_num, unit, False, False, False, chain_len, n_families)
+        res, t = self.alloc_result(scene, 0, 0, n_families, caps0)
+        self.trace_device(scene, rays_t, prm, res, max_live)
+        cnt = t["counters"].cpu().numpy()
+        self._raise_status(cnt)
+        nseg = int(cnt[A.C_SEGMENTS]) if record_segments else 0
+        nhit = int(cnt[A.C_HITS]) if record_hits else 0
+        # pass 2: record
+        prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families)
+        res, t = self.alloc_result(scene, nseg, nhit, n_families, caps0)
+        self.trace_device(scene, rays_t, prm, res, max_live)
+        torch.cuda.synchronize(self.device)
+        out = {k: v.cpu().numpy() for k, v in t.items()}
+        for k in A.SEG_U32 + A.HIT_U32:
+            out[k] = out[k].view(np.uint32)
+        self._raise_status(out["counters"])
+        if record_segments and nseg:
+            order = np.lexsort((out["seg_pop"], out["seg_root"]))
+            for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32:
+                out[k] = out[k][order]
+        if record_hits and nhit:
+            order = np.lexsort((out["hit_pop"], out["hit_monitor"], out["hit_root"]))
+            for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64:
+                out[k] = out[k][order]
+        return out
+
+    @staticmethod
+    def _raise_status(counters):
+        st = int(counters[A.C_STATUS])
+        if st & A.ST_WORK_OVERFLOW:
+            raise BackendError("wavefront workspace overflow: pass a larger max_live")
+        if st & (A.ST_SEG_OVERFLOW | A.ST_HIT_OVERFLOW):
+            raise BackendError("result capacity overflow")

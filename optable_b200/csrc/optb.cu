@@ -1,0 +1,836 @@
+// optb.cu -- C-ABI CUDA library (include/optb.h) for the optable bounce loop on B200 (sm_100a).
+//
+// Kernels:
+//   trace_kernel      whole bounce loop. One thread owns one ray of the current wavefront; warps pull 32-ray
+//                     chunks from a global work counter (persistent grid). The scene tables are staged into
+//                     shared memory with a TMA bulk copy (cp.async.bulk + mbarrier). A root whose alive set
+//                     is a single ray keeps bouncing in registers (closest hit -> physics -> monitors ->
+//                     next bounce); split interactions park their children in a sparse slot pair.
+//   tile_sums/scan_sums/scatter   ordered stream compaction of the children into the next wavefront
+//                     (order = reference BFS order, which the pop cap of optical_table.py:86-97 needs).
+//   mark_kernel       first/last wavefront index of every root (rank of a ray inside its root's generation).
+// Segments and monitor rows are appended with warp-aggregated atomics and carry their (root, pop) key.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "optb_device.cuh"
+
+using namespace optb;
+
+namespace {
+
+constexpr int kBlock = 128;
+constexpr int kTile = 2048;  // children-scan tile (entries per block)
+constexpr int kScanBlock = 256;
+constexpr int kRayF64 = 13;
+
+// SoA ray storage in the workspace (wavefront W and sparse children C)
+struct RayBuf {
+  double* f[kRayF64];  // ox oy oz dx dy dz I wl qre qim pl n len
+  uint32_t* flags; uint32_t* root; uint32_t* pop; int32_t* family;
+};
+
+struct Header {  // first bytes of the workspace
+  unsigned int work_ctr;
+  unsigned int n_next;
+  unsigned int pad[14];
+};
+
+struct SceneOff { uint32_t nf, ni, matk, matf, mon, aux; };
+
+struct TraceArgs {
+  const unsigned char* blob; uint32_t blob_bytes; SceneOff off; int n_nodes, n_mons;
+  // input wavefront: either the caller's rays (gen0) or the workspace wavefront
+  optb_rays in0; RayBuf w; int gen0;
+  long long n_in; const unsigned int* n_in_dev;  // n_in_dev overrides when non-null
+  const uint32_t* gen_first; const uint32_t* gen_last;
+  // split output
+  RayBuf c; uint8_t* nchild;
+  // params
+  long long max_trace; double unit; int rec_seg, rec_hit, rec_hist, chain_len, n_families, fam_shared;
+  int hist_smem;
+  optb_result out;
+  unsigned long long* counters;
+  Header* hdr;
+};
+
+OPTB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+OPTB_DEV void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+OPTB_DEV void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+OPTB_DEV void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+OPTB_DEV void mbar_wait(unsigned long long* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
+OPTB_DEV unsigned long long warp_alloc(unsigned long long* ctr) {
+  unsigned m = __activemask();
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(ctr, (unsigned long long)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+OPTB_DEV void load_ray(const TraceArgs& a, long long i, Ray& r, bool& solo, uint32_t& gcount) {
+  if (a.gen0) {
+    const optb_rays& s = a.in0;
+    r.ox = s.ox[i]; r.oy = s.oy[i]; r.oz = s.oz[i];
+    r.dx = s.dx[i]; r.dy = s.dy[i]; r.dz = s.dz[i];
+    r.I = s.intensity[i]; r.wl = s.wavelength[i]; r.qre = s.q_re[i]; r.qim = s.q_im[i];
+    r.pl = s.pathlength[i]; r.n = s.n_medium[i];
+    r.len = s.length ? s.length[i] : INFINITY;
+    r.flags = s.flags ? s.flags[i] : (OPTB_RF_ALIVE | OPTB_RF_HASQ);
+    r.root = (uint32_t)i; r.pop = 0;
+    r.family = s.family ? s.family[i] : (int32_t)i;
+    solo = true; gcount = 1;
+  } else {
+    const RayBuf& w = a.w;
+    r.ox = w.f[0][i]; r.oy = w.f[1][i]; r.oz = w.f[2][i];
+    r.dx = w.f[3][i]; r.dy = w.f[4][i]; r.dz = w.f[5][i];
+    r.I = w.f[6][i]; r.wl = w.f[7][i]; r.qre = w.f[8][i]; r.qim = w.f[9][i];
+    r.pl = w.f[10][i]; r.n = w.f[11][i]; r.len = w.f[12][i];
+    r.flags = w.flags[i]; r.root = w.root[i]; r.family = w.family[i];
+    uint32_t first = a.gen_first[r.root], last = a.gen_last[r.root];
+    gcount = last - first + 1;
+    solo = (gcount == 1);
+    r.pop = w.pop[i] + (uint32_t)(i - first);  // pop_base of this generation + rank inside the root
+  }
+}
+
+OPTB_DEV void store_child(const RayBuf& c, long long j, const Ray& parent, const Children& ch, int k, uint32_t pop_base) {
+  c.f[0][j] = ch.ox; c.f[1][j] = ch.oy; c.f[2][j] = ch.oz;
+  c.f[3][j] = ch.dx[k]; c.f[4][j] = ch.dy[k]; c.f[5][j] = ch.dz[k];
+  c.f[6][j] = ch.I[k]; c.f[7][j] = parent.wl; c.f[8][j] = ch.qre[k]; c.f[9][j] = ch.qim[k];
+  c.f[10][j] = ch.pl; c.f[11][j] = ch.nmed[k]; c.f[12][j] = parent.len;
+  c.flags[j] = parent.flags; c.root[j] = parent.root; c.pop[j] = pop_base; c.family[j] = parent.family;
+}
+
+// One pop's dead segment: append to the segment log and test it against every monitor (monitor.py:183-193).
+OPTB_DEV void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& r, double seg_len, uint32_t seg_flags,
+                           int leaf, unsigned int* s_hist, unsigned long long& n_hits_local) {
+  if (a.rec_seg) {
+    unsigned long long j = warp_alloc(&a.counters[OPTB_C_SEGMENTS]);
+    if (j < (unsigned long long)a.out.seg_capacity) {
+      const optb_result& o = a.out;
+      o.seg_ox[j] = r.ox; o.seg_oy[j] = r.oy; o.seg_oz[j] = r.oz;
+      o.seg_dx[j] = r.dx; o.seg_dy[j] = r.dy; o.seg_dz[j] = r.dz;
+      o.seg_length[j] = seg_len; o.seg_intensity[j] = r.I; o.seg_wavelength[j] = r.wl;
+      o.seg_q_re[j] = r.qre; o.seg_q_im[j] = r.qim; o.seg_pathlength[j] = r.pl; o.seg_n[j] = r.n;
+      o.seg_flags[j] = seg_flags; o.seg_root[j] = r.root; o.seg_pop[j] = r.pop; o.seg_leaf[j] = leaf;
+    } else {
+      atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_SEG_OVERFLOW);
+    }
+  }
+  for (int m = 0; m < sv.n_mons; m++) {
+    const double* mf = sv.mon + m * OPTB_MON_STRIDE;
+    double ox, oy, oz, dx, dy, dz;
+    to_local(mf + OPTB_MON_ORIGIN, mf + OPTB_MON_TINV, r, ox, oy, oz, dx, dy, dz);
+    if (dx == 0.0) continue;
+    double t = -ox / dx;
+    if (!(t >= 1e-9) || t > seg_len) continue;
+    double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+    if (!(fabs(Py) <= mf[OPTB_MON_HW] && fabs(Pz) <= mf[OPTB_MON_HH])) continue;
+    if (a.rec_hist) {
+      double y = dot3(Px, Py, Pz, mf[OPTB_MON_TY], mf[OPTB_MON_TY + 1], mf[OPTB_MON_TY + 2]);
+      double z = dot3(Px, Py, Pz, mf[OPTB_MON_TZ], mf[OPTB_MON_TZ + 1], mf[OPTB_MON_TZ + 2]);
+      int by = hist_bin(y, -mf[OPTB_MON_HW], mf[OPTB_MON_HW]);
+      int bz = hist_bin(z, -mf[OPTB_MON_HH], mf[OPTB_MON_HH]);
+      const int per = OPTB_HIST_BINS * (OPTB_HIST_BINS + 1);
+      if (by >= 0) {
+        if (a.hist_smem) {
+          atomicAdd(&s_hist[m * per + by], 1u);
+          if (bz >= 0) atomicAdd(&s_hist[m * per + OPTB_HIST_BINS + by * OPTB_HIST_BINS + bz], 1u);
+        } else {
+          atomicAdd((unsigned long long*)&a.out.hist_y[m * OPTB_HIST_BINS + by], 1ull);
+          if (bz >= 0)
+            atomicAdd((unsigned long long*)&a.out.hist_yz[(m * OPTB_HIST_BINS + by) * OPTB_HIST_BINS + bz], 1ull);
+        }
+      }
+    }
+    if (a.rec_hit) {
+      unsigned long long j = warp_alloc(&a.counters[OPTB_C_HITS]);
+      if (j < (unsigned long long)a.out.hit_capacity) {
+        const optb_result& o = a.out;
+        o.hit_monitor[j] = m; o.hit_root[j] = r.root; o.hit_pop[j] = r.pop;
+        o.hit_px[j] = Px; o.hit_py[j] = Py; o.hit_pz[j] = Pz;
+        o.hit_intensity[j] = r.I; o.hit_t[j] = t;
+        o.hit_dx[j] = r.dx; o.hit_dy[j] = r.dy; o.hit_dz[j] = r.dz;
+        o.hit_q_re[j] = r.qre; o.hit_q_im[j] = r.qim;
+      } else {
+        atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_HIT_OVERFLOW);
+      }
+    } else {
+      n_hits_local++;
+    }
+  }
+}
+
+// Closest hit over the flattened tree (optical_table.py:119-123 + component_group.py:93-122).
+OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
+                          double& best_t, int& best_node, unsigned long long& tests) {
+  best_t = INFINITY; best_node = -1;
+  if (!(ray.flags & OPTB_RF_ALIVE)) return;  // optical_component.py:349-350
+  int i = 0;
+  const int n = sv.n_nodes;
+  while (i < n) {
+    const int32_t* ni = sv.ni + i * OPTB_NI_STRIDE;
+    const double* nf = sv.nf + i * OPTB_NF_STRIDE;
+    if (ni[OPTB_NI_AABB]) {
+      double t1, t2;
+      if (!slab(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, nf + OPTB_NF_AABB, t1, t2)) { i = ni[OPTB_NI_SKIP]; continue; }
+    }
+    if (ni[OPTB_NI_GEOM] == OPTB_G_GROUP) { i++; continue; }
+    double ox, oy, oz, dx, dy, dz;
+    to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);
+    tests++;
+    double t = intersect_leaf(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len);
+    if (t >= 0.0) {
+      bool ok = true;
+      int slot = ni[OPTB_NI_CAPSLOT];
+      if (slot >= 0) {  // should_interact / increase_interact_count :136-149, 359-362
+        int32_t* cnt = a.out.cap_counts + (long long)slot * a.n_families + ray.family;
+        int old = atomicAdd(cnt, 1);
+        if (!((double)old < nf[OPTB_NF_CAPMAX])) {
+          atomicSub(cnt, 1);
+          ok = false;
+          if (!solo || a.fam_shared) atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_CAP_ORDER);
+        }
+      }
+      if (ok && t < best_t) { best_t = t; best_node = i; }
+    }
+    i++;
+  }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ TraceArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const unsigned char* base = a.blob;
+  if constexpr (SMEM) {
+    // Stage the whole scene blob with TMA bulk copies; completion is signalled on the mbarrier.
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&mbar, a.blob_bytes);
+      constexpr uint32_t kChunk = 32768;
+      for (uint32_t off = 0; off < a.blob_bytes; off += kChunk)
+        tma_bulk_g2s(smem_raw + off, a.blob + off, min(kChunk, a.blob_bytes - off), &mbar);
+    }
+    mbar_wait(&mbar, 0);
+    base = smem_raw;
+  }
+  SceneView sv;
+  sv.nf = (const double*)(base + a.off.nf);
+  sv.ni = (const int32_t*)(base + a.off.ni);
+  sv.matk = (const int32_t*)(base + a.off.matk);
+  sv.matf = (const double*)(base + a.off.matf);
+  sv.mon = (const double*)(base + a.off.mon);
+  sv.aux = (const double*)(base + a.off.aux);
+  sv.n_nodes = a.n_nodes; sv.n_mons = a.n_mons;
+
+  const int per = OPTB_HIST_BINS * (OPTB_HIST_BINS + 1);
+  unsigned int* s_hist = (unsigned int*)(smem_raw + (SMEM ? ((a.blob_bytes + 15u) & ~15u) : 0u));
+  if (a.hist_smem) {
+    for (int k = threadIdx.x; k < a.n_mons * per; k += blockDim.x) s_hist[k] = 0u;
+    __syncthreads();
+  }
+
+  const long long n_in = a.n_in_dev ? (long long)*a.n_in_dev : a.n_in;
+  const int lane = threadIdx.x & 31;
+  unsigned long long c_pops = 0, c_inter = 0, c_tests = 0, c_drop = 0, c_hits = 0;
+
+  while (true) {
+    unsigned int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(&a.hdr->work_ctr, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    long long i = (long long)chunk * 32 + lane;
+    if ((long long)chunk * 32 >= n_in) break;
+    if (i >= n_in) continue;
+
+    Ray ray; bool solo; uint32_t gcount;
+    load_ray(a, i, ray, solo, gcount);
+    const uint32_t pop_base_next = a.gen0 ? 0u : (a.w.pop[i] + gcount);
+    int nch = 0;
+    int chained = 0;
+    Children ch;
+    ch.n = 0;
+    while (true) {
+      if ((long long)ray.pop >= a.max_trace) { c_drop++; nch = 0; break; }  // queued but never popped
+      double t; int node;
+      closest_hit(a, sv, ray, solo, t, node, c_tests);
+      c_pops++;
+      if (node < 0) {  // optical_table.py:132-134: the ray itself, untouched
+        emit_segment(a, sv, ray, ray.len, ray.flags, -1, s_hist, c_hits);
+        nch = 0;
+        break;
+      }
+      const int32_t* ni = sv.ni + node * OPTB_NI_STRIDE;
+      const double* nf = sv.nf + node * OPTB_NF_STRIDE;
+      emit_segment(a, sv, ray, t, ray.flags & ~OPTB_RF_ALIVE, ni[OPTB_NI_LEAF], s_hist, c_hits);
+      c_inter++;
+      double ox, oy, oz, dx, dy, dz;
+      to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);
+      interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch);
+      nch = ch.n;
+      if (nch == 1 && solo && (a.chain_len == 0 || chained + 1 < a.chain_len)) {
+        // the root's alive set is this one ray: BFS order is trivially kept, continue in registers
+        ray.ox = ch.ox; ray.oy = ch.oy; ray.oz = ch.oz;
+        ray.dx = ch.dx[0]; ray.dy = ch.dy[0]; ray.dz = ch.dz[0];
+        ray.I = ch.I[0]; ray.qre = ch.qre[0]; ray.qim = ch.qim[0]; ray.pl = ch.pl; ray.n = ch.nmed[0];
+        ray.pop++; chained++;
+        continue;
+      }
+      break;
+    }
+    if (a.nchild) {
+      a.nchild[i] = (uint8_t)nch;
+      uint32_t pb = solo ? ray.pop + 1u : pop_base_next;
+      for (int k = 0; k < nch; k++) store_child(a.c, 2 * i + k, ray, ch, k, pb);
+    }
+  }
+
+  // counters: warp reduce then one atomic per warp
+  unsigned long long v[5] = {c_pops, c_inter, c_tests, c_drop, c_hits};
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], s);
+  }
+  if (lane == 0) {
+    if (!a.rec_seg && v[0]) atomicAdd(&a.counters[OPTB_C_SEGMENTS], v[0]);
+    if (v[1]) atomicAdd(&a.counters[OPTB_C_INTERACTIONS], v[1]);
+    if (v[2]) atomicAdd(&a.counters[OPTB_C_TESTS], v[2]);
+    if (v[3]) atomicAdd(&a.counters[OPTB_C_DROPPED], v[3]);
+    if (!a.rec_hit && v[4]) atomicAdd(&a.counters[OPTB_C_HITS], v[4]);
+  }
+  if (a.hist_smem) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.n_mons * per; k += blockDim.x) {
+      unsigned int cnt = s_hist[k];
+      if (!cnt) continue;
+      int m = k / per, r = k % per;
+      if (r < OPTB_HIST_BINS) atomicAdd((unsigned long long*)&a.out.hist_y[m * OPTB_HIST_BINS + r], (unsigned long long)cnt);
+      else atomicAdd((unsigned long long*)&a.out.hist_yz[m * OPTB_HIST_BINS * OPTB_HIST_BINS + (r - OPTB_HIST_BINS)],
+                     (unsigned long long)cnt);
+    }
+  }
+}
+
+// ---- ordered compaction of the sparse children into the next wavefront --------------------------------
+__global__ void __launch_bounds__(kScanBlock) tile_sums_kernel(const uint8_t* __restrict__ nchild, long long n,
+                                                               unsigned int* __restrict__ sums) {
+  __shared__ unsigned int s[kScanBlock / 32];
+  long long base = (long long)blockIdx.x * kTile;
+  unsigned int acc = 0;
+  for (int k = threadIdx.x; k < kTile; k += kScanBlock) {
+    long long i = base + k;
+    if (i < n) acc += nchild[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int w = 0; w < kScanBlock / 32; w++) t += s[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of the tile sums in place; total -> hdr->n_next; also resets the work counter
+__global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restrict__ sums, int ntiles, Header* hdr,
+                                                         unsigned long long* counters, unsigned int capacity) {
+  __shared__ unsigned int s[1024];
+  __shared__ unsigned int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < ntiles; b0 += 1024) {
+    int idx = b0 + threadIdx.x;
+    unsigned int v = idx < ntiles ? sums[idx] : 0u;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      unsigned int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    unsigned int incl = s[threadIdx.x];
+    if (idx < ntiles) sums[idx] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned int total = carry;
+    if (total > capacity) {
+      atomicOr(&counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_WORK_OVERFLOW);
+      total = 0;  // stop cleanly
+    }
+    hdr->n_next = total;
+    hdr->work_ctr = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kScanBlock) scatter_kernel(const uint8_t* __restrict__ nchild, long long n,
+                                                             const unsigned int* __restrict__ tile_base, RayBuf c, RayBuf w,
+                                                             const Header* hdr) {
+  __shared__ unsigned int s_warp[kScanBlock / 32];
+  if (hdr->n_next == 0) return;
+  constexpr int kPer = kTile / kScanBlock;  // consecutive entries per thread
+  long long i0 = (long long)blockIdx.x * kTile + (long long)threadIdx.x * kPer;
+  unsigned int cnt[kPer];
+  unsigned int mine = 0;
+#pragma unroll
+  for (int k = 0; k < kPer; k++) {
+    long long i = i0 + k;
+    cnt[k] = (i < n) ? nchild[i] : 0u;
+    mine += cnt[k];
+  }
+  // block exclusive scan of `mine`
+  unsigned int incl = mine;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  unsigned int woff = 0;
+  for (int k = 0; k < wid; k++) woff += s_warp[k];
+  unsigned int off = tile_base[blockIdx.x] + woff + incl - mine;
+#pragma unroll
+  for (int k = 0; k < kPer; k++) {
+    long long i = i0 + k;
+    for (unsigned int j = 0; j < cnt[k]; j++) {
+      long long src = 2 * i + j;
+      long long dst = off++;
+#pragma unroll
+      for (int f = 0; f < kRayF64; f++) w.f[f][dst] = c.f[f][src];
+      w.flags[dst] = c.flags[src]; w.root[dst] = c.root[src]; w.pop[dst] = c.pop[src]; w.family[dst] = c.family[src];
+    }
+  }
+}
+
+__global__ void mark_kernel(const uint32_t* __restrict__ root, const Header* hdr, uint32_t* __restrict__ gen_first,
+                            uint32_t* __restrict__ gen_last) {
+  long long n = hdr->n_next;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    uint32_t r = root[j];
+    if (j == 0 || root[j - 1] != r) gen_first[r] = (uint32_t)j;
+    if (j == n - 1 || root[j + 1] != r) gen_last[r] = (uint32_t)j;
+  }
+}
+
+__global__ void finish_kernel(unsigned long long* counters, unsigned long long gens, unsigned long long launches) {
+  counters[OPTB_C_GENERATIONS] = gens;
+  counters[OPTB_C_LAUNCHES] = launches;
+}
+
+// FP64 FMA peak probe: 8 independent chains per thread
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-6;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+// ---- host side ----------------------------------------------------------------------------------------
+struct optb_ctx {
+  int device;
+  int sm_count;
+  size_t smem_optin;
+  char err[512];
+  // arena for optb_trace_host
+  void* arena; size_t arena_bytes;
+  unsigned long long* h_counters;  // pinned
+  unsigned int* h_hdr;             // pinned
+};
+
+struct optb_scene {
+  unsigned char* d_blob; uint32_t blob_bytes; SceneOff off;
+  int n_nodes, n_leaves, n_mats, n_mons, n_caps; long long n_aux;
+  int max_children;
+  bool in_smem; bool hist_smem; uint32_t smem_bytes;
+};
+
+static int fail(optb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    if (e != cudaSuccess) snprintf(ctx->err, sizeof ctx->err, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(ctx->err, sizeof ctx->err, "%s", what);
+  }
+  return code;
+}
+#define CK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(ctx, -10, what, e__); } while (0)
+
+extern "C" int optb_abi_version(void) { return OPTB_ABI_VERSION; }
+
+extern "C" int optb_ctx_create(int device, optb_ctx** out) {
+  if (!out) return -1;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) return -2;
+  optb_ctx* ctx = new (std::nothrow) optb_ctx();
+  if (!ctx) return -3;
+  memset(ctx, 0, sizeof *ctx);
+  ctx->device = device;
+  cudaSetDevice(device);
+  cudaDeviceProp p;
+  cudaGetDeviceProperties(&p, device);
+  ctx->sm_count = p.multiProcessorCount;
+  ctx->smem_optin = p.sharedMemPerBlockOptin;
+  cudaMallocHost((void**)&ctx->h_counters, sizeof(unsigned long long) * OPTB_C_COUNT);
+  cudaMallocHost((void**)&ctx->h_hdr, sizeof(Header));
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int optb_ctx_destroy(optb_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
+  delete ctx;
+  return 0;
+}
+
+extern "C" const char* optb_last_error(const optb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_scene** out) {
+  if (!ctx || !d || !out) return -1;
+  if (d->abi_version != OPTB_ABI_VERSION) return fail(ctx, -4, "scene ABI version mismatch");
+  if (d->n_nodes < 0 || d->n_materials < 1) return fail(ctx, -5, "bad scene counts");
+  cudaSetDevice(ctx->device);
+  optb_scene* s = new (std::nothrow) optb_scene();
+  if (!s) return -3;
+  memset(s, 0, sizeof *s);
+  s->n_nodes = d->n_nodes; s->n_leaves = d->n_leaves; s->n_mats = d->n_materials; s->n_mons = d->n_monitors;
+  s->n_caps = d->n_capslots; s->n_aux = d->n_aux;
+  size_t b_nf = (size_t)d->n_nodes * OPTB_NF_STRIDE * 8, b_ni = (size_t)d->n_nodes * OPTB_NI_STRIDE * 4;
+  size_t b_mk = (size_t)d->n_materials * 4, b_mf = (size_t)d->n_materials * OPTB_MF_STRIDE * 8;
+  size_t b_mon = (size_t)std::max(d->n_monitors, 1) * OPTB_MON_STRIDE * 8, b_aux = (size_t)std::max<long long>(d->n_aux, 1) * 8;
+  size_t o = 0;
+  s->off.nf = (uint32_t)o; o = align_up(o + b_nf, 16);
+  s->off.ni = (uint32_t)o; o = align_up(o + b_ni, 16);
+  s->off.matk = (uint32_t)o; o = align_up(o + b_mk, 16);
+  s->off.matf = (uint32_t)o; o = align_up(o + b_mf, 16);
+  s->off.mon = (uint32_t)o; o = align_up(o + b_mon, 16);
+  s->off.aux = (uint32_t)o; o = align_up(o + b_aux, 16);
+  if (o > 0xfff00000ull) { delete s; return fail(ctx, -6, "scene too large"); }
+  s->blob_bytes = (uint32_t)o;
+  std::vector<unsigned char> host(o, 0);
+  if (d->n_nodes) {
+    memcpy(host.data() + s->off.nf, d->node_f, b_nf);
+    memcpy(host.data() + s->off.ni, d->node_i, b_ni);
+  }
+  memcpy(host.data() + s->off.matk, d->mat_kind, b_mk);
+  memcpy(host.data() + s->off.matf, d->mat_f, b_mf);
+  if (d->n_monitors) memcpy(host.data() + s->off.mon, d->mon_f, (size_t)d->n_monitors * OPTB_MON_STRIDE * 8);
+  if (d->n_aux) memcpy(host.data() + s->off.aux, d->aux, (size_t)d->n_aux * 8);
+  // most children one interaction can emit (decides whether the wavefront machinery is needed)
+  int mc = 0;
+  for (int i = 0; i < d->n_nodes; i++) {
+    const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
+    const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
+    int k = 0;
+    switch (ni[OPTB_NI_INTER]) {
+      case OPTB_I_MIRROR: k = (nf[OPTB_NF_REFL] > 0) + (nf[OPTB_NF_TRANS] > 0); break;
+      case OPTB_I_REFRACT: k = nf[OPTB_NF_REFL] > 0 ? 2 : 1; break;
+      case OPTB_I_THINLENS: k = 1; break;
+      default: k = 0;
+    }
+    mc = std::max(mc, k);
+  }
+  s->max_children = mc;
+  size_t hist_bytes = (size_t)d->n_monitors * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 4;
+  size_t budget = ctx->smem_optin > 2048 ? ctx->smem_optin - 2048 : 0;
+  s->in_smem = (o <= budget);
+  size_t used = s->in_smem ? o : 0;
+  s->hist_smem = (hist_bytes > 0 && used + hist_bytes <= std::min<size_t>(budget, used + 65536));
+  s->smem_bytes = (uint32_t)(used + (s->hist_smem ? hist_bytes : 0));
+  cudaError_t e = cudaMalloc((void**)&s->d_blob, o);
+  if (e != cudaSuccess) { delete s; return fail(ctx, -10, "cudaMalloc(scene)", e); }
+  e = cudaMemcpy(s->d_blob, host.data(), o, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(s->d_blob); delete s; return fail(ctx, -10, "cudaMemcpy(scene)", e); }
+  *out = s;
+  return 0;
+}
+
+extern "C" int optb_scene_destroy(optb_ctx* ctx, optb_scene* s) {
+  if (!s) return 0;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (s->d_blob) cudaFree(s->d_blob);
+  delete s;
+  return 0;
+}
+
+namespace {
+struct WsLayout {
+  size_t hdr, w, c, nchild, gen_first, gen_last, sums, total;
+  long long cap;  // wavefront capacity (rays)
+};
+size_t raybuf_bytes(long long cap) { return align_up((size_t)cap * 8, 256) * kRayF64 + align_up((size_t)cap * 4, 256) * 4; }
+WsLayout ws_layout(long long n_rays, long long max_live, bool split) {
+  WsLayout L{};
+  size_t o = 0;
+  L.hdr = o; o += align_up(sizeof(Header), 256);
+  L.cap = split ? std::max(max_live, n_rays) : 0;
+  if (split) {
+    L.w = o; o += raybuf_bytes(L.cap);
+    L.c = o; o += raybuf_bytes(2 * L.cap);
+    L.nchild = o; o += align_up((size_t)L.cap, 256);
+    L.gen_first = o; o += align_up((size_t)n_rays * 4, 256);
+    L.gen_last = o; o += align_up((size_t)n_rays * 4, 256);
+    L.sums = o; o += align_up(((size_t)L.cap / kTile + 2) * 4, 256);
+  }
+  L.total = o;
+  return L;
+}
+RayBuf make_raybuf(unsigned char* base, long long cap) {
+  RayBuf b;
+  size_t o = 0;
+  for (int f = 0; f < kRayF64; f++) { b.f[f] = (double*)(base + o); o += align_up((size_t)cap * 8, 256); }
+  b.flags = (uint32_t*)(base + o); o += align_up((size_t)cap * 4, 256);
+  b.root = (uint32_t*)(base + o); o += align_up((size_t)cap * 4, 256);
+  b.pop = (uint32_t*)(base + o); o += align_up((size_t)cap * 4, 256);
+  b.family = (int32_t*)(base + o);
+  return b;
+}
+bool needs_wavefront(const optb_scene* s, const optb_params* p) { return s->max_children > 1 || p->chain_len > 0; }
+}  // namespace
+
+extern "C" int64_t optb_workspace_bytes(const optb_scene* scene, int64_t n_rays, int64_t max_live) {
+  if (!scene || n_rays < 0) return -1;
+  // the caller may later pass chain_len > 0, so always size for the wavefront when asked for max_live > 0
+  bool split = scene->max_children > 1 || max_live > 0;
+  return (int64_t)ws_layout(n_rays, std::max<int64_t>(max_live, n_rays), split).total;
+}
+
+extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
+                          optb_result* out, void* workspace, int64_t workspace_bytes, void* stream_v) {
+  if (!ctx || !scene || !rays || !prm || !out) return -1;
+  cudaStream_t st = (cudaStream_t)stream_v;
+  cudaSetDevice(ctx->device);
+  if (!out->counters) return fail(ctx, -7, "result.counters is required");
+  if (rays->n >= 0xffffffffll) return fail(ctx, -7, "at most 2^32-1 rays per call");
+  if (scene->n_caps > 0 && (!out->cap_counts || prm->n_families < 1)) return fail(ctx, -7, "scene has interact caps: cap_counts/n_families required");
+  const bool split = needs_wavefront(scene, prm);
+  WsLayout L = ws_layout(rays->n, 0, false);
+  long long cap = 0;
+  if (split) {
+    // find the largest wavefront capacity the given workspace supports
+    if (workspace_bytes < (int64_t)ws_layout(rays->n, rays->n, true).total) return fail(ctx, -8, "workspace too small (see optb_workspace_bytes)");
+    long long lo = rays->n, hi = std::max<long long>(rays->n, 1) * 64;
+    while (lo < hi) {
+      long long mid = lo + (hi - lo + 1) / 2;
+      if ((int64_t)ws_layout(rays->n, mid, true).total <= workspace_bytes) lo = mid; else hi = mid - 1;
+    }
+    cap = lo;
+    L = ws_layout(rays->n, cap, true);
+  } else if (workspace_bytes < (int64_t)L.total) {
+    return fail(ctx, -8, "workspace too small (see optb_workspace_bytes)");
+  }
+  unsigned char* ws = (unsigned char*)workspace;
+  Header* hdr = (Header*)(ws + L.hdr);
+
+  CK(cudaMemsetAsync(out->counters, 0, sizeof(int64_t) * OPTB_C_COUNT, st), "memset counters");
+  CK(cudaMemsetAsync(hdr, 0, sizeof(Header), st), "memset header");
+  if (prm->record_hist && scene->n_mons) {
+    if (!out->hist_y || !out->hist_yz) return fail(ctx, -7, "record_hist needs hist_y and hist_yz");
+    CK(cudaMemsetAsync(out->hist_y, 0, sizeof(int64_t) * OPTB_HIST_BINS * scene->n_mons, st), "memset hist");
+    CK(cudaMemsetAsync(out->hist_yz, 0, sizeof(int64_t) * OPTB_HIST_BINS * OPTB_HIST_BINS * scene->n_mons, st), "memset hist");
+  }
+
+  TraceArgs a;
+  memset(&a, 0, sizeof a);
+  a.blob = scene->d_blob; a.blob_bytes = scene->blob_bytes; a.off = scene->off;
+  a.n_nodes = scene->n_nodes; a.n_mons = scene->n_mons;
+  a.in0 = *rays; a.gen0 = 1; a.n_in = rays->n; a.n_in_dev = nullptr;
+  a.max_trace = prm->max_trace_num; a.unit = prm->unit;
+  a.rec_seg = prm->record_segments; a.rec_hit = prm->record_hits; a.rec_hist = prm->record_hist && scene->n_mons > 0;
+  a.chain_len = prm->chain_len; a.n_families = prm->n_families;
+  a.fam_shared = (rays->family != nullptr);
+  a.hist_smem = a.rec_hist && scene->hist_smem;
+  a.out = *out;
+  a.counters = (unsigned long long*)out->counters;
+  a.hdr = hdr;
+  if (split) {
+    a.w = make_raybuf(ws + L.w, cap);
+    a.c = make_raybuf(ws + L.c, 2 * cap);
+    a.nchild = ws + L.nchild;
+    a.gen_first = (uint32_t*)(ws + L.gen_first);
+    a.gen_last = (uint32_t*)(ws + L.gen_last);
+  }
+  uint32_t smem = scene->in_smem ? scene->smem_bytes : (a.hist_smem ? scene->smem_bytes : 0);
+  auto kern = scene->in_smem ? trace_kernel<true> : trace_kernel<false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
+  int occ = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem), "occupancy");
+  if (occ < 1) occ = 1;
+  const int full_grid = ctx->sm_count * occ;
+
+  unsigned long long gens = 0, launches = 0;
+  long long n_in = rays->n;
+  while (n_in > 0) {
+    long long want = (n_in + kBlock - 1) / kBlock;
+    int grid = (int)std::min<long long>(full_grid, want);
+    a.n_in = n_in;
+    void* kargs[] = {(void*)&a};
+    CK(cudaLaunchKernel((const void*)kern, dim3(grid), dim3(kBlock), kargs, smem, st), "launch trace_kernel");
+    launches++; gens++;
+    if (!split) break;
+    int ntiles = (int)((n_in + kTile - 1) / kTile);
+    unsigned int* sums = (unsigned int*)(ws + L.sums);
+    tile_sums_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, n_in, sums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, ntiles, hdr, a.counters, (unsigned int)std::min<long long>(cap, 0xffffffffll));
+    scatter_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, n_in, sums, a.c, a.w, hdr);
+    mark_kernel<<<std::min(full_grid * 2, std::max(1, (int)((2 * n_in + 255) / 256))), 256, 0, st>>>(a.w.root, hdr, (uint32_t*)a.gen_first, (uint32_t*)a.gen_last);
+    launches += 4;
+    CK(cudaMemcpyAsync(ctx->h_hdr, hdr, sizeof(Header), cudaMemcpyDeviceToHost, st), "read header");
+    CK(cudaStreamSynchronize(st), "sync generation");
+    n_in = ((Header*)ctx->h_hdr)->n_next;
+    a.gen0 = 0;
+  }
+  finish_kernel<<<1, 1, 0, st>>>(a.counters, gens, launches + 1);
+  CK(cudaGetLastError(), "kernel launch");
+  return 0;
+}
+
+namespace {
+struct ArenaCursor {
+  unsigned char* base; size_t off, cap;
+  void* take(size_t bytes) { size_t o = align_up(off, 256); off = o + bytes; return off <= cap ? base + o : nullptr; }
+};
+}  // namespace
+
+extern "C" int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
+                               optb_result* out) {
+  if (!ctx || !scene || !rays || !prm || !out) return -1;
+  cudaSetDevice(ctx->device);
+  const int64_t n = rays->n;
+  const bool split = needs_wavefront(scene, prm);
+  const int64_t segcap = prm->record_segments ? out->seg_capacity : 0, hitcap = prm->record_hits ? out->hit_capacity : 0;
+  const int64_t max_live = split ? std::max<int64_t>(4 * n, 1024) : 0;
+  const int64_t wsb = (int64_t)ws_layout(n, max_live, split).total;
+  const int nfam = std::max(prm->n_families, 1);
+  size_t need = 256 * 64 + (size_t)n * (8 * 13 + 8) + (size_t)segcap * (13 * 8 + 16) + (size_t)hitcap * (10 * 8 + 12) +
+                (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 8 +
+                (size_t)std::max(scene->n_caps, 1) * nfam * 4 + 64 * 8 + (size_t)wsb;
+  if (ctx->arena_bytes < need) {
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr; ctx->arena_bytes = 0;
+    CK(cudaMalloc(&ctx->arena, need), "cudaMalloc(arena)");
+    ctx->arena_bytes = need;
+  }
+  ArenaCursor ac{(unsigned char*)ctx->arena, 0, ctx->arena_bytes};
+  cudaStream_t st = 0;
+  optb_rays dr = *rays;
+  const double* const* src_f = &rays->ox;
+  const double** dst_f = &dr.ox;
+  for (int f = 0; f < kRayF64; f++) {
+    if (!src_f[f]) { dst_f[f] = nullptr; continue; }
+    void* d = ac.take((size_t)n * 8);
+    if (!d) return fail(ctx, -9, "arena sizing");
+    CK(cudaMemcpyAsync(d, src_f[f], (size_t)n * 8, cudaMemcpyHostToDevice, st), "H2D rays");
+    dst_f[f] = (const double*)d;
+  }
+  if (rays->flags) { void* d = ac.take((size_t)n * 4); CK(cudaMemcpyAsync(d, rays->flags, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D flags"); dr.flags = (const uint32_t*)d; }
+  if (rays->family) { void* d = ac.take((size_t)n * 4); CK(cudaMemcpyAsync(d, rays->family, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D family"); dr.family = (const int32_t*)d; }
+  optb_result dv = *out;
+  struct Col { void** dev; void* host; size_t elt; int64_t cap; int kind; };  // kind 0 seg, 1 hit
+  std::vector<Col> cols;
+  auto add = [&](void** dev_field, void* host_ptr, size_t elt, int64_t capn, int kind) {
+    if (!host_ptr || capn == 0) { *dev_field = nullptr; return; }
+    *dev_field = ac.take((size_t)capn * elt);
+    cols.push_back({dev_field, host_ptr, elt, capn, kind});
+  };
+  double** seg_d = &dv.seg_ox; double* const* seg_h = &out->seg_ox;
+  for (int f = 0; f < 13; f++) add((void**)&seg_d[f], seg_h[f], 8, segcap, 0);
+  add((void**)&dv.seg_flags, out->seg_flags, 4, segcap, 0); add((void**)&dv.seg_root, out->seg_root, 4, segcap, 0);
+  add((void**)&dv.seg_pop, out->seg_pop, 4, segcap, 0); add((void**)&dv.seg_leaf, out->seg_leaf, 4, segcap, 0);
+  add((void**)&dv.hit_monitor, out->hit_monitor, 4, hitcap, 1); add((void**)&dv.hit_root, out->hit_root, 4, hitcap, 1);
+  add((void**)&dv.hit_pop, out->hit_pop, 4, hitcap, 1);
+  double** hit_d = &dv.hit_px; double* const* hit_h = &out->hit_px;
+  for (int f = 0; f < 10; f++) add((void**)&hit_d[f], hit_h[f], 8, hitcap, 1);
+  for (auto& c : cols) if (!*c.dev) return fail(ctx, -9, "arena sizing");
+  const size_t hy = (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * 8, hyz = hy * OPTB_HIST_BINS;
+  dv.hist_y = (int64_t*)ac.take(hy); dv.hist_yz = (int64_t*)ac.take(hyz);
+  const size_t capb = (size_t)std::max(scene->n_caps, 1) * nfam * 4;
+  dv.cap_counts = (int32_t*)ac.take(capb);
+  dv.counters = (int64_t*)ac.take(OPTB_C_COUNT * 8);
+  void* ws = ac.take((size_t)wsb);
+  if (!ws || !dv.counters) return fail(ctx, -9, "arena sizing");
+  if (scene->n_caps > 0 && out->cap_counts) CK(cudaMemcpyAsync(dv.cap_counts, out->cap_counts, capb, cudaMemcpyHostToDevice, st), "H2D caps");
+  int rc = optb_trace(ctx, scene, &dr, prm, &dv, ws, wsb, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_counters, dv.counters, OPTB_C_COUNT * 8, cudaMemcpyDeviceToHost, st), "D2H counters");
+  CK(cudaStreamSynchronize(st), "sync trace");
+  if (out->counters) memcpy(out->counters, ctx->h_counters, OPTB_C_COUNT * 8);
+  int64_t nseg = std::min<int64_t>((int64_t)ctx->h_counters[OPTB_C_SEGMENTS], segcap);
+  int64_t nhit = std::min<int64_t>((int64_t)ctx->h_counters[OPTB_C_HITS], hitcap);
+  for (auto& c : cols) {
+    int64_t rows = c.kind == 0 ? nseg : nhit;
+    if (rows > 0) CK(cudaMemcpyAsync(c.host, *c.dev, (size_t)rows * c.elt, cudaMemcpyDeviceToHost, st), "D2H results");
+  }
+  if (prm->record_hist && scene->n_mons) {
+    if (out->hist_y) CK(cudaMemcpyAsync(out->hist_y, dv.hist_y, (size_t)scene->n_mons * OPTB_HIST_BINS * 8, cudaMemcpyDeviceToHost, st), "D2H hist");
+    if (out->hist_yz) CK(cudaMemcpyAsync(out->hist_yz, dv.hist_yz, (size_t)scene->n_mons * OPTB_HIST_BINS * OPTB_HIST_BINS * 8, cudaMemcpyDeviceToHost, st), "D2H hist");
+  }
+  if (scene->n_caps > 0 && out->cap_counts) CK(cudaMemcpyAsync(out->cap_counts, dv.cap_counts, capb, cudaMemcpyDeviceToHost, st), "D2H caps");
+  CK(cudaStreamSynchronize(st), "sync results");
+  return 0;
+}
+
+extern "C" int optb_measure_fp64_peak(optb_ctx* ctx, double* tflops_out) {
+  if (!ctx || !tflops_out) return -1;
+  cudaSetDevice(ctx->device);
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 16;
+  double* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(double) * blocks * threads), "cudaMalloc");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  dfma_kernel<<<blocks, threads>>>(d, 1024);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    dfma_kernel<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaError_t e = cudaGetLastError();
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, -10, "dfma kernel", e);
+  double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  return 0;
+}

@@ -1,0 +1,499 @@
+// optb_device.cuh -- device-side geometry and physics of the optable bounce loop (fp64, sm_100a).
+//
+// Semantics follow the reference decision by decision (tolerances, branch order, tie-breaks); the
+// arithmetic is re-derived for the GPU (closed-form roots under the reference's own sign-scan,
+// reciprocal-multiply normalisation, Horner polynomials) and agrees to ~1e-13 relative.
+// Reference citations are relative to /root/reference/optable/.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/optb.h"
+
+#define OPTB_DEV __device__ __forceinline__
+
+namespace optb {
+
+struct Ray {
+  double ox, oy, oz, dx, dy, dz;
+  double I, wl, qre, qim, pl, n, len;
+  uint32_t flags, root, pop;
+  int32_t family;
+};
+
+// Pointers into the staged scene tables (shared memory when they fit, else global/L2).
+struct SceneView {
+  const double* nf;
+  const int32_t* ni;
+  const int32_t* matk;
+  const double* matf;
+  const double* mon;
+  const double* aux;
+  int n_nodes, n_mons;
+};
+
+OPTB_DEV double dot3(double ax, double ay, double az, double bx, double by, double bz) {
+  return fma(ax, bx, fma(ay, by, az * bz));
+}
+
+// ray_to_local_coordinates optical_component.py:106-111 (+ direction setter ray.py:115-119)
+OPTB_DEV void to_local(const double* __restrict__ c, const double* __restrict__ Ti, const Ray& r,
+                       double& ox, double& oy, double& oz, double& dx, double& dy, double& dz) {
+  double vx = r.ox - c[0], vy = r.oy - c[1], vz = r.oz - c[2];
+  ox = dot3(Ti[0], Ti[1], Ti[2], vx, vy, vz);
+  oy = dot3(Ti[3], Ti[4], Ti[5], vx, vy, vz);
+  oz = dot3(Ti[6], Ti[7], Ti[8], vx, vy, vz);
+  double ex = dot3(Ti[0], Ti[1], Ti[2], r.dx, r.dy, r.dz);
+  double ey = dot3(Ti[3], Ti[4], Ti[5], r.dx, r.dy, r.dz);
+  double ez = dot3(Ti[6], Ti[7], Ti[8], r.dx, r.dy, r.dz);
+  double rn = rsqrt(dot3(ex, ey, ez, ex, ey, ez));
+  dx = ex * rn; dy = ey * rn; dz = ez * rn;
+}
+
+// solve_ray_bboxes_intersections solver.py:5-48, one box
+OPTB_DEV bool slab(double ox, double oy, double oz, double dx, double dy, double dz,
+                   const double* __restrict__ bb, double& t1o, double& t2o) {
+  double t1 = 0.0, t2 = INFINITY;
+  const double o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    double bmin = bb[2 * ax], bmax = bb[2 * ax + 1];
+    if (fabs(d[ax]) <= 1e-8) {  // np.isclose(d, 0.0)
+      if (o[ax] < bmin || o[ax] > bmax) { t1 = 1.0; t2 = 0.0; }
+    } else {
+      double inv = 1.0 / d[ax];
+      double ta = (bmin - o[ax]) * inv, tb = (bmax - o[ax]) * inv;
+      t1 = fmax(t1, fmin(ta, tb));
+      t2 = fmin(t2, fmax(ta, tb));
+    }
+  }
+  t1o = t1; t2o = t2;
+  return (t2 + 1e-12 >= t1) && (t2 >= 0.0);
+}
+
+// ---- ASphere profile (component_group.py:1065-1107) ----
+// The reference differentiates this profile numerically (h = 1e-4 radius, surfaces.py:351-369); the second
+// difference amplifies every rounding of f by ~1e8, so the operation order of the Python closure is kept
+// exactly and FMA contraction is ruled out with the _rn intrinsics.
+OPTB_DEV double f_asphere(int form, const double* __restrict__ c, double r) {
+  double r2 = __dmul_rn(r, r);
+  if (form == OPTB_ASPH_PARAMETRIC) {
+    // r**2 / (R * (1 + sqrt(1 - (1 + kappa) * (r**2) / (R**2)))) + a4 r**4 + a6 r**6 + a8 r**8
+    double R = c[0];
+    double u = __ddiv_rn(__dmul_rn(__dadd_rn(1.0, c[1]), r2), __dmul_rn(R, R));
+    double s = __dsqrt_rn(__dsub_rn(1.0, u));
+    double acc = __ddiv_rn(r2, __dmul_rn(R, __dadd_rn(1.0, s)));
+    double r4 = __dmul_rn(r2, r2);
+    acc = __dadd_rn(acc, __dmul_rn(c[2], r4));
+    acc = __dadd_rn(acc, __dmul_rn(c[3], __dmul_rn(r4, r2)));
+    acc = __dadd_rn(acc, __dmul_rn(c[4], __dmul_rn(r4, r4)));
+    return acc;
+  }
+  // (EFL / (n + 1)) * (-1 + sqrt(1 + (n + 1) / (n - 1) * (r**2) / (EFL**2)))
+  double EFL = c[0], n = c[1];
+  double u = __ddiv_rn(__dmul_rn(__ddiv_rn(__dadd_rn(n, 1.0), __dsub_rn(n, 1.0)), r2), __dmul_rn(EFL, EFL));
+  return __dmul_rn(__ddiv_rn(EFL, __dadd_rn(n, 1.0)), __dadd_rn(-1.0, __dsqrt_rn(__dadd_rn(1.0, u))));
+}
+
+// ---- Polygon.within_boundary surfaces.py:534-558 ----
+OPTB_DEV bool poly_within(const double* __restrict__ rec, double Px, double Py, double Pz) {
+  const double tol = 1e-9;
+  int nv = (int)rec[0];
+  const double* v = rec + OPTB_POLY_HEADER;
+  double ex = Px - rec[4], ey = Py - rec[5], ez = Pz - rec[6];
+  double px = dot3(ex, ey, ez, rec[7], rec[8], rec[9]);
+  double py = dot3(ex, ey, ez, rec[10], rec[11], rec[12]);
+  bool inside = false;
+  for (int i = 0; i < nv; i++) {
+    int j = (i + 1 == nv) ? 0 : i + 1;
+    double x1 = v[2 * i], y1 = v[2 * i + 1], x2 = v[2 * j], y2 = v[2 * j + 1];
+    double cr = (x2 - x1) * (py - y1) - (y2 - y1) * (px - x1);
+    if (fabs(cr) <= tol && fmin(x1, x2) - tol <= px && px <= fmax(x1, x2) + tol &&
+        fmin(y1, y2) - tol <= py && py <= fmax(y1, y2) + tol)
+      return true;
+    if ((y1 > py) != (y2 > py)) {
+      double x_at_y = x1 + (py - y1) * (x2 - x1) / (y2 - y1);
+      if (x_at_y >= px) inside = !inside;
+    }
+  }
+  return inside;
+}
+
+OPTB_DEV bool planar_within(const SceneView& sv, int kind, double p0, double p1, double Px, double Py, double Pz) {
+  if (kind == OPTB_G_CIRCLE) return sqrt(dot3(Px, Py, Pz, Px, Py, Pz)) <= p0;  // surfaces.py:144-145 (3-D norm)
+  if (kind == OPTB_G_RECT) return fabs(Py) <= p0 && fabs(Pz) <= p1;            // surfaces.py:170-171
+  if (kind == OPTB_G_POLY2D) return poly_within(sv.aux + (long long)p0, Px, Py, Pz);
+  return false;
+}
+
+// surface within_boundary for curved kinds (surfaces.py:230-235, 300-303, 390-393)
+OPTB_DEV bool curved_within(const SceneView& sv, int g, const int32_t* __restrict__ ni, const double* __restrict__ p,
+                            double Px, double Py, double Pz) {
+  if (g == OPTB_G_SPHERE) return (p[0] - p[1] - 1e-12 <= Px) && (Px <= p[0] + 1e-12);
+  if (g == OPTB_G_ASPHERE) return sqrt(Py * Py + Pz * Pz) <= p[0] + 1e-12;
+  if (g == OPTB_G_CYL) {
+    double th = atan2(Py, Px);
+    return (p[2] <= th && th <= p[3]) && (-p[1] / 2 <= Pz && Pz <= p[1] / 2);
+  }
+  return poly_within(sv.aux + ni[OPTB_NI_AUX], Px, Py, Pz);  // POLY3D
+}
+
+// scipy brentq restated (xtol 2e-12, rtol 4 eps, maxiter 100) for the asphere profile
+struct AsphF {
+  int form; const double* c;
+  double ox, oy, oz, dx, dy, dz;
+  OPTB_DEV double operator()(double t) const {
+    double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+    return Px + f_asphere(form, c, sqrt(Py * Py + Pz * Pz));  // ASphere.f surfaces.py:375-378
+  }
+};
+
+template <class F>
+OPTB_DEV double brentq(const F& f, double xa, double xb, double fa, double fb) {
+  const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+  double xpre = xa, xcur = xb, xblk = 0., fpre = fa, fcur = fb, fblk = 0., spre = 0., scur = 0.;
+  if (fpre == 0) return xpre;
+  if (fcur == 0) return xcur;
+  for (int i = 0; i < 100; i++) {
+    if (fpre != 0 && fcur != 0 && (signbit(fpre) != signbit(fcur))) {
+      xblk = xpre; fblk = fpre; spre = scur = xcur - xpre;
+    }
+    if (fabs(fblk) < fabs(fcur)) {
+      xpre = xcur; xcur = xblk; xblk = xpre;
+      fpre = fcur; fcur = fblk; fblk = fpre;
+    }
+    double delta = (xtol + rtol * fabs(xcur)) / 2;
+    double sbis = (xblk - xcur) / 2;
+    if (fcur == 0 || fabs(sbis) < delta) return xcur;
+    if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+      double stry;
+      if (xpre == xblk) {
+        stry = -fcur * (xcur - xpre) / (fcur - fpre);
+      } else {
+        double dpre = (fpre - fcur) / (xpre - xcur);
+        double dblk = (fblk - fcur) / (xblk - xcur);
+        stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+      }
+      if (2 * fabs(stry) < fmin(fabs(spre), 3 * fabs(sbis) - delta)) { spre = scur; scur = stry; }
+      else { spre = sbis; scur = sbis; }
+    } else {
+      spre = sbis; scur = sbis;
+    }
+    xpre = xcur; fpre = fcur;
+    if (fabs(scur) > delta) xcur += scur;
+    else xcur += (sbis > 0 ? delta : -delta);
+    fcur = f(xcur);
+  }
+  return xcur;
+}
+
+// np.linspace(a, b, 10)[i]
+OPTB_DEV double sample_t(int i, double a, double b, double step) { return i == 9 ? b : fma((double)i, step, a); }
+
+// intersect_point_local optical_component.py:151-233 for one leaf, local-frame ray. Returns t or -1.
+OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
+                               double ox, double oy, double oz, double dx, double dy, double dz, double len) {
+  const int g = ni[OPTB_NI_GEOM];
+  const double* p = nf + OPTB_NF_P;
+  if (g == OPTB_G_CIRCLE || g == OPTB_G_RECT || g == OPTB_G_POLY2D || g == OPTB_G_CSG) {
+    // planar branch :165-196: plane x = 0
+    if (dx == 0.0) return -1.0;          // parallel: miss, or t = 0 which |t| < EPS rejects
+    double t = -ox / dx;
+    if (!(t >= 1e-9) || t > len) return -1.0;  // |t|<EPS, t<0, t>length, NaN
+    double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+    bool in;
+    if (g == OPTB_G_CSG) {
+      bool a = planar_within(sv, (int)p[1], p[2], p[3], Px, Py, Pz);
+      bool b = planar_within(sv, (int)p[4], p[5], p[6], Px, Py, Pz);
+      in = ((int)p[0] == 0) ? (a && !b) : (a || b);
+    } else if (g == OPTB_G_POLY2D) {
+      in = poly_within(sv.aux + ni[OPTB_NI_AUX], Px, Py, Pz);
+    } else {
+      in = planar_within(sv, g, p[0], p[1], Px, Py, Pz);
+    }
+    return in ? t : -1.0;
+  }
+  // curved branch :197-233. Local AABB (Surface.get_bbox_local) -> bracket -> 10-point sign scan -> roots.
+  double bb[6];
+  if (g == OPTB_G_SPHERE) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) bb[i] = p[2 + i];
+  } else if (g == OPTB_G_ASPHERE) {
+    bb[0] = p[6]; bb[1] = p[7]; bb[2] = -p[0]; bb[3] = p[0]; bb[4] = -p[0]; bb[5] = p[0];
+  } else if (g == OPTB_G_CYL) {
+    bb[0] = -p[0]; bb[1] = p[0]; bb[2] = -p[0]; bb[3] = p[0]; bb[4] = -p[1] / 2; bb[5] = p[1] / 2;
+  } else {
+    const double* rec = sv.aux + ni[OPTB_NI_AUX];
+#pragma unroll
+    for (int i = 0; i < 6; i++) bb[i] = rec[13 + i];
+  }
+  double t1, t2;
+  slab(ox, oy, oz, dx, dy, dz, bb, t1, t2);
+  if (t2 + 1e-9 < t1) return -1.0;
+  t1 = fmax(t1, 0.0);
+  t2 = fmin(t2, 100.0);
+  const double a = t1 - 1e-9, b = t2 + 1e-9;
+  const double step = (b - a) / 9.0;
+  // roots found by the sign scan, ascending in t (sub-intervals are visited in order)
+  double r0 = -1.0, r1 = -1.0;  // at most two admissible roots are ever needed before the boundary test
+  int nroot = 0;
+  if (g == OPTB_G_ASPHERE) {
+    AsphF f{ni[OPTB_NI_AUX], p + 1, ox, oy, oz, dx, dy, dz};
+    double ta = a, fa = f(a);
+    for (int i = 1; i < 10; i++) {
+      double tb = sample_t(i, a, b, step), fb = f(tb);
+      if (fa * fb < 0) {
+        double r = brentq(f, ta, tb, fa, fb);
+        if (r >= 1e-9 && r <= len) {  // t >= 0 and |t| >= EPS and t <= length
+          // first admissible root inside the aperture wins; later ones only matter if this one fails
+          double Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
+          if (sqrt(Py * Py + Pz * Pz) <= p[0] + 1e-12) {
+            if (b >= a) return r;  // ascending scan: this is the smallest admissible root
+            if (nroot == 0 || r < r0) r0 = r;
+            nroot = 1;
+          }
+        }
+      }
+      ta = tb; fa = fb;
+    }
+    return nroot ? r0 : -1.0;
+  }
+  // Quadratic / linear surfaces: g(t) has the sign of Surface.f(o + t d); closed-form roots.
+  double A, B, Cc;  // g(t) = A t^2 + 2 B t + C
+  if (g == OPTB_G_SPHERE) {          // f = |P| - R            surfaces.py:294-295
+    A = 1.0; B = dot3(ox, oy, oz, dx, dy, dz); Cc = dot3(ox, oy, oz, ox, oy, oz) - p[0] * p[0];
+  } else if (g == OPTB_G_CYL) {      // f = |P_xy| - r         surfaces.py:224-225
+    A = fma(dx, dx, dy * dy); B = fma(ox, dx, oy * dy); Cc = fma(ox, ox, oy * oy) - p[0] * p[0];
+  } else {                           // 3-D polygon: f = n.(P - v0), linear       surfaces.py:530-532
+    const double* rec = sv.aux + ni[OPTB_NI_AUX];
+    A = 0.0;
+    B = 0.5 * dot3(rec[1], rec[2], rec[3], dx, dy, dz);
+    Cc = dot3(rec[1], rec[2], rec[3], ox - rec[4], oy - rec[5], oz - rec[6]);
+  }
+  double lo, hi;  // the two real roots (lo <= hi) or NaN
+  if (A != 0.0) {
+    double disc = fma(B, B, -A * Cc);
+    if (!(disc >= 0.0)) return -1.0;  // g never changes sign
+    double sq = sqrt(disc);
+    double qv = -(B + copysign(sq, B));
+    double ra = qv / A, rb = (qv != 0.0) ? Cc / qv : ra;
+    lo = fmin(ra, rb); hi = fmax(ra, rb);
+  } else {
+    if (B == 0.0) return -1.0;
+    lo = hi = -Cc / (2.0 * B);
+  }
+  double ta = a, ga = fma(fma(A, a, 2.0 * B), a, Cc);
+  double best = -1.0;
+  for (int i = 1; i < 10; i++) {
+    double tb = sample_t(i, a, b, step);
+    double gb = fma(fma(A, tb, 2.0 * B), tb, Cc);
+    if (ga * gb < 0) {
+      // exactly one root of g inside this sub-interval: entering (g: + -> -) is `lo`, leaving is `hi`
+      double r;
+      if (A != 0.0) r = ((ga > 0) == (tb > ta)) ? lo : hi;
+      else r = lo;
+      if (r >= 1e-9 && r <= len) {
+        double Px = fma(r, dx, ox), Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
+        if (curved_within(sv, g, ni, p, Px, Py, Pz)) {
+          if (b >= a) return r;
+          if (best < 0 || r < best) best = r;
+        }
+      }
+    }
+    ta = tb; ga = gb;
+  }
+  return best;
+}
+
+// Surface.normal at a local hit point
+OPTB_DEV void surf_normal(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
+                          double Px, double Py, double Pz, double& nx, double& ny, double& nz, double& roc_fd) {
+  const int g = ni[OPTB_NI_GEOM];
+  const double* p = nf + OPTB_NF_P;
+  roc_fd = INFINITY;
+  if (g == OPTB_G_SPHERE) { double ir = 1.0 / p[0]; nx = Px * ir; ny = Py * ir; nz = Pz * ir; return; }
+  if (g == OPTB_G_CYL) { double ir = 1.0 / p[0]; nx = Px * ir; ny = Py * ir; nz = 0.0; return; }
+  if (g == OPTB_G_ASPHERE) {
+    // central differences with h = 1e-4 * radius  surfaces.py:351-388
+    double r = __dsqrt_rn(__dadd_rn(__dmul_rn(Py, Py), __dmul_rn(Pz, Pz)));
+    double h = 1e-4 * p[0];
+    int form = ni[OPTB_NI_AUX];
+    double fp = f_asphere(form, p + 1, r + h), fm = f_asphere(form, p + 1, r - h);
+    double d1 = (fp - fm) / (2 * h);
+    if (ni[OPTB_NI_ROCKIND] == OPTB_ROC_ASPHERE_FD) {
+      double f0 = f_asphere(form, p + 1, r);
+      double d2 = (fp - 2 * f0 + fm) / (h * h);
+      double w = 1.0 + d1 * d1;
+      roc_fd = w * sqrt(w) / d2;  // (1 + f'^2)^1.5 / f''
+    }
+    if (r < 1e-12) { nx = 1.0; ny = 0.0; nz = 0.0; return; }
+    double ir = 1.0 / r;
+    double ax = 1.0, ay = d1 * (Py * ir), az = d1 * (Pz * ir);
+    double rn = rsqrt(dot3(ax, ay, az, ax, ay, az));
+    nx = ax * rn; ny = ay * rn; nz = az * rn;
+    return;
+  }
+  if (g == OPTB_G_POLY2D || g == OPTB_G_POLY3D) {
+    const double* rec = sv.aux + ni[OPTB_NI_AUX];
+    nx = rec[1]; ny = rec[2]; nz = rec[3];
+    return;
+  }
+  nx = 1.0; ny = 0.0; nz = 0.0;
+}
+
+// Material.n / SellmeierMaterial.sellmeier_n material.py:12-21, 106-120
+OPTB_DEV double material_n(const SceneView& sv, int m, double wl_m) {
+  const double* f = sv.matf + m * OPTB_MF_STRIDE;
+  if (sv.matk[m] == OPTB_MAT_CONST) return f[0];
+  double wl_um = wl_m / 1e-6;
+  double w2 = wl_um * wl_um;
+  double n2 = 1.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) n2 += f[i] * w2 / (w2 - f[3 + i]);
+  return sqrt(n2);
+}
+
+// numpy complex128 division (Smith)
+OPTB_DEV void cdiv(double a, double b, double c, double d, double& re, double& im) {
+  if (fabs(c) >= fabs(d)) {
+    double r = d / c, den = fma(d, r, c);
+    double id = 1.0 / den;
+    re = fma(b, r, a) * id; im = fma(-a, r, b) * id;
+  } else {
+    double r = c / d, den = fma(c, r, d);
+    double id = 1.0 / den;
+    re = fma(a, r, b) * id; im = fma(b, r, -a) * id;
+  }
+}
+
+// What one interaction emits: both children start at the same lab point.
+struct Children {
+  int n;
+  double ox, oy, oz;    // lab origin
+  double pl;            // _pathlength of the children
+  double dx[2], dy[2], dz[2], I[2], qre[2], qim[2], nmed[2];
+};
+
+// local child direction -> lab (ray_to_lab_coordinates :119-124; both normalisations)
+OPTB_DEV void dir_to_lab(const double* __restrict__ T, double lx, double ly, double lz, double& gx, double& gy, double& gz) {
+  double rn = rsqrt(dot3(lx, ly, lz, lx, ly, lz));
+  lx *= rn; ly *= rn; lz *= rn;
+  double ex = dot3(T[0], T[1], T[2], lx, ly, lz);
+  double ey = dot3(T[3], T[4], T[5], lx, ly, lz);
+  double ez = dot3(T[6], T[7], T[8], lx, ly, lz);
+  double r2 = rsqrt(dot3(ex, ey, ez, ex, ey, ez));
+  gx = ex * r2; gy = ey * r2; gz = ez * r2;
+}
+
+// interact_local bodies for the winning leaf. (ox..dz) is the ray in the leaf's local frame, t the hit parameter.
+OPTB_DEV void interact(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
+                       const Ray& ray, double unit, double ox, double oy, double oz, double dx, double dy, double dz,
+                       double t, Children& ch) {
+  const double* T = nf + OPTB_NF_T;
+  const double* c = nf + OPTB_NF_ORIGIN;
+  double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+  ch.n = 0;
+  ch.ox = dot3(T[0], T[1], T[2], Px, Py, Pz) + c[0];
+  ch.oy = dot3(T[3], T[4], T[5], Px, Py, Pz) + c[1];
+  ch.oz = dot3(T[6], T[7], T[8], Px, Py, Pz) + c[2];
+  const bool hasq = (ray.flags & OPTB_RF_HASQ) != 0;
+  const int kind = ni[OPTB_NI_INTER];
+  const double refl = nf[OPTB_NF_REFL], trans = nf[OPTB_NF_TRANS];
+  ch.pl = fma(t, ray.n, ray.pl);  // Ray.pathlength ray.py:145-147
+  if (kind == OPTB_I_ABSORB) return;  // Block :501-503
+  if (kind == OPTB_I_THINLENS) {      // Lens :930-948
+    double f = nf[OPTB_NF_FOCAL];
+    double qre = ray.qre, qim = ray.qim;
+    if (hasq) {
+      double q1r = ray.qre + t, q1i = ray.qim;
+      cdiv(q1r, q1i, 1.0 - q1r / f, -(q1i / f), qre, qim);
+    }
+    double inv_f = 1.0 / f;
+    dir_to_lab(T, dx - Px * inv_f, dy - Py * inv_f, dz - Pz * inv_f, ch.dx[0], ch.dy[0], ch.dz[0]);
+    ch.I[0] = ray.I * trans; ch.qre[0] = qre; ch.qim[0] = qim; ch.nmed[0] = ray.n;
+    ch.pl = ray.pl;  // the thin lens leaves _pathlength untouched
+    ch.n = 1;
+    return;
+  }
+  double nx, ny, nz, roc_fd;
+  surf_normal(sv, ni, nf, Px, Py, Pz, nx, ny, nz, roc_fd);
+  double dn = dot3(dx, dy, dz, nx, ny, nz);
+  if (kind == OPTB_I_MIRROR) {  // BaseMirror :536-570, children [reflected, transmitted]
+    double qre = ray.qre + t, qim = ray.qim;
+    int k = 0;
+    if (refl > 0) {
+      dir_to_lab(T, fma(-2 * dn, nx, dx), fma(-2 * dn, ny, dy), fma(-2 * dn, nz, dz), ch.dx[k], ch.dy[k], ch.dz[k]);
+      ch.I[k] = ray.I * refl; ch.qre[k] = qre; ch.qim[k] = qim; ch.nmed[k] = ray.n; k++;
+    }
+    if (trans > 0) {
+      dir_to_lab(T, dx, dy, dz, ch.dx[k], ch.dy[k], ch.dz[k]);
+      ch.I[k] = ray.I * trans; ch.qre[k] = qre; ch.qim[k] = qim; ch.nmed[k] = ray.n; k++;
+    }
+    ch.n = k;
+    return;
+  }
+  // BaseRefraciveSurface :617-717, children [transmitted | TIR, reflected]
+  double wl_m = ray.wl * unit;
+  double n1 = material_n(sv, ni[OPTB_NI_MAT1], wl_m);
+  double n2 = material_n(sv, ni[OPTB_NI_MAT2], wl_m);
+  double ROC = INFINITY;
+  int rk = ni[OPTB_NI_ROCKIND];
+  if (rk == OPTB_ROC_CONST) ROC = nf[OPTB_NF_ROC];
+  else if (rk == OPTB_ROC_ASPHERE_FD) ROC = roc_fd;
+  double nin, nout;
+  if (dn < 0) { nin = n1; nout = n2; }
+  else { nin = n2; nout = n1; ROC = -ROC; }
+  double qtr = 0, qti = 0, qrr = 0, qri = 0;
+  if (hasq) {
+    double qr = ray.qre + t, qi = ray.qim;
+    double Cc = (nin - nout) / (ROC * nout), D = nin / nout;
+    cdiv(qr, qi, fma(Cc, qr, D), Cc * qi, qtr, qti);
+    double C2 = 2.0 / ROC;
+    cdiv(qr, qi, fma(C2, qr, 1.0), C2 * qi, qrr, qri);
+  }
+  double rtx = fma(-dn, nx, dx), rty = fma(-dn, ny, dy), rtz = fma(-dn, nz, dz);
+  double sgn = dn > 0 ? 1.0 : -1.0;
+  double cos_i = fmin(fmax(dn, -1.0), 1.0);
+  double sin_i = sqrt(1.0 - cos_i * cos_i);
+  double sin_t = (nin * sin_i) / nout;
+  // reflected direction d + 2 cos_i (-n)
+  double rfx = fma(-2 * cos_i, nx, dx), rfy = fma(-2 * cos_i, ny, dy), rfz = fma(-2 * cos_i, nz, dz);
+  int k = 0;
+  if (sin_t < 1) {
+    if (trans > 0) {
+      double cos_t = sqrt(1.0 - sin_t * sin_t);
+      double kk = nin / nout, cs = cos_t * sgn;
+      dir_to_lab(T, fma(kk, rtx, cs * nx), fma(kk, rty, cs * ny), fma(kk, rtz, cs * nz), ch.dx[k], ch.dy[k], ch.dz[k]);
+      ch.I[k] = ray.I * trans; ch.qre[k] = qtr; ch.qim[k] = qti; ch.nmed[k] = nout; k++;
+    }
+  } else {  // total internal reflection (also taken when sin_t is NaN, as `sin_t < 1` is False)
+    dir_to_lab(T, rfx, rfy, rfz, ch.dx[k], ch.dy[k], ch.dz[k]);
+    ch.I[k] = ray.I; ch.qre[k] = qrr; ch.qim[k] = qri; ch.nmed[k] = ray.n; k++;
+  }
+  if (refl > 0) {
+    if (k == 1 && !(sin_t < 1)) {  // TIR + reflectivity: same direction twice
+      ch.dx[1] = ch.dx[0]; ch.dy[1] = ch.dy[0]; ch.dz[1] = ch.dz[0];
+    } else {
+      dir_to_lab(T, rfx, rfy, rfz, ch.dx[k], ch.dy[k], ch.dz[k]);
+    }
+    ch.I[k] = ray.I * refl; ch.qre[k] = qrr; ch.qim[k] = qri; ch.nmed[k] = ray.n; k++;
+  }
+  ch.n = k;
+}
+
+// np.histogram(x, bins=30, range=(lo, hi)) bin index, -1 outside
+OPTB_DEV int hist_bin(double x, double lo, double hi) {
+  const int nb = OPTB_HIST_BINS;
+  if (!(x >= lo && x <= hi)) return -1;
+  double norm = nb / (hi - lo);
+  int idx = (int)((x - lo) * norm);
+  if (idx == nb) idx = nb - 1;
+  double step = (hi - lo) / nb;
+  double e0 = fma((double)idx, step, lo);
+  double e1 = (idx + 1 == nb) ? hi : fma((double)(idx + 1), step, lo);
+  if (x < e0) idx--;
+  else if (x >= e1 && idx != nb - 1) idx++;
+  return idx;
+}
+
+}  // namespace optb

@@ -136,7 +136,7 @@ class FlatScene:
             self.mon_f[k, A.MON_TZ:A.MON_TZ + 3] = T @ np.array([0.0, 0.0, 1.0])
         self.n_nodes = self.node_i.shape[0]
         self.n_leaves = len(self.leaves)
-        self.n_materials = len(self._mats.kind)
+        self.n_materials = int(self.mat_kind.shape[0])  # >= 1 (a dummy row when nothing refracts)
         self.n_monitors = len(self.monitors)
         self.n_capslots = len(self.capslots)
 
@@ -277,6 +277,31 @@ class FlatScene:
         else:
             raise FlattenError(f"component class {type(comp).__name__} has no device interaction")
         self.max_children = max(self.max_children, nchild)
+
+    # -- (de)serialisation: the tables alone define the device scene ------------------------------
+    TABLES = ("node_i", "node_f", "mat_kind", "mat_f", "mon_f", "aux")
+
+    def to_arrays(self) -> dict:
+        d = {k: getattr(self, k) for k in self.TABLES}
+        d["counts"] = np.array([self.n_leaves, self.n_materials, self.n_monitors, self.n_capslots, self.max_children],
+                               dtype=np.int64)
+        return d
+
+    @classmethod
+    def from_arrays(cls, d) -> "FlatScene":
+        self = cls.__new__(cls)
+        self.node_i = np.ascontiguousarray(d["node_i"], dtype=np.int32).reshape(-1, A.NI_STRIDE)
+        self.node_f = np.ascontiguousarray(d["node_f"], dtype=np.float64).reshape(-1, A.NF_STRIDE)
+        self.mat_kind = np.ascontiguousarray(d["mat_kind"], dtype=np.int32)
+        self.mat_f = np.ascontiguousarray(d["mat_f"], dtype=np.float64)
+        self.mon_f = np.ascontiguousarray(d["mon_f"], dtype=np.float64)
+        self.aux = np.ascontiguousarray(d["aux"], dtype=np.float64)
+        c = [int(v) for v in d["counts"]]
+        self.n_leaves, self.n_materials, self.n_monitors, self.n_capslots, self.max_children = c
+        self.n_nodes = self.node_i.shape[0]
+        self.n_materials = int(self.mat_kind.shape[0])
+        self.leaves, self.capslots, self.monitors = [], [], []
+        return self
 
     # -- ABI view ----------------------------------------------------------------------------
     def desc(self) -> A.SceneDesc:
