@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the optable ray_tracing hot path on B200 (contract: see the repo brief / DESIGN.md section 6).
+
+  python bench.py --gpus N --steps K --warmup W          # CUDA arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --steps K --warmup W  # CPU arm: oracle port of the reference, all host threads
+
+Workload (BASELINE.json configs[1]): two LENS-9 parametric aspheres as a 4f relay, monitors at
+x = 0 and x = 2F1 + 2F2, 1e7 synthetic collimated Gaussian rays per GPU (disc radius 3, splitmix64 positions).
+A step = one trace of the whole batch incl. monitor row capture. Metric = ray-surface interactions per second
+(an interaction = one popped ray that hit a surface = one output segment of finite length).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ray-surface interactions/sec (fp64)"
+UNIT = "interactions/s"
+WORKLOAD = "c2_4f_telescope"
+BYTES_PER_INTERACTION = 208  # read + write one 104-B ray record per interaction (wavefront form)
+# fp64 flops per interaction of this workload, from the ncu instruction counts of profiles/ 
+FLOPS_PER_INTERACTION = None
+
+
+def build_scene():
+    import optable_b200 as ob
+    from optable_b200.flatten import FlatScene
+    from tests import scenes
+
+    sc = scenes.telescope_4f(ob, n_rays=0)
+    return FlatScene(sc.components, sc.monitors)
+
+
+def make_bundle(n, start):
+    from optable_b200.bundle import RayBundle
+
+    return RayBundle.collimated_disc(n, start=start, x0=-10.0, radius=3.0, wavelength=780e-7, w0=61e-4)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.05)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows for k in range(4) if len(r) >= 6 and r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_arm(flat, n_sample, threads, repeats=1):
+    """Oracle port of the reference on the host cores: interactions/s on the first n_sample rays of the workload."""
+    from oracle import oracle as O
+
+    arrs = make_bundle(n_sample, 0).materialise()
+    best = None
+    inter = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = O.trace(flat, arrs, record_segments=False, record_hits=False, nthreads=threads)
+        dt = time.perf_counter() - t0
+        inter = int(out["counters"][1])
+        best = dt if best is None else min(best, dt)
+    return inter / best, inter, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    flat = build_scene()
+    threads = os.cpu_count() or 1
+    n_sample = args.ref_rays
+    for _ in range(args.warmup):
+        cpu_arm(flat, max(n_sample // 10, 1000), threads)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        _, inter, _ = cpu_arm(flat, n_sample, threads)
+        total += inter
+    dt = time.perf_counter() - t0
+    value = total / dt
+    sample = f"first {n_sample} rays of the {WORKLOAD} batch per step, oracle/optb_oracle.c (C port of the reference), {threads} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step": n_sample, "surfaces": int(flat.n_leaves), "monitors": int(flat.n_monitors)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    from optable_b200 import _abi as A
+    from optable_b200.backend import Engine
+    from optable_b200.bundle import DeviceTrace
+    from optable_b200.flatten import rays_struct
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    engine = Engine.get(local)
+    flat = build_scene()
+    n = args.rays
+    bundle = make_bundle(n, start=rank * n)  # weak scaling: every rank traces its own n rays of the endless bundle
+    rays_dev = bundle.to_torch(device=dev)
+    hit_cap = n * flat.n_monitors
+    dt = DeviceTrace(engine, flat, n, hit_cap, record_hist=True)
+    stream = torch.cuda.current_stream()
+
+    def merge_monitors():
+        # the only cross-GPU exchange of the path: monitor histograms (+ row counts); rows stay sharded
+        if world > 1:
+            dist.all_reduce(dt.t["hist_y"])
+            dist.all_reduce(dt.t["hist_yz"])
+
+    def step():
+        dt.run(rays_dev)
+        merge_monitors()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    cnt = dt.counters()
+    engine._raise_status(cnt)
+    inter_per_step, hits_per_step = int(cnt[A.C_INTERACTIONS]), int(cnt[A.C_HITS])
+    launches_per_step = int(cnt[A.C_LAUNCHES])
+    # ---- timed region: device-resident inputs, CUDA events on the launching stream, max over ranks ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kern_ms = []
+    ev[0].record(stream)
+    for k in range(args.steps):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        dt.run(rays_dev)
+        k1.record(stream)
+        merge_monitors()
+        ev[k + 1].record(stream)
+        kern_ms.append((k0, k1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    trace_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
+    clocks = sampler.stop()
+    if world > 1:
+        tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total_ms = float(tm.item())
+        ti = torch.tensor([inter_per_step], device=dev, dtype=torch.int64)
+        dist.all_reduce(ti)
+        inter_all = int(ti.item())
+    else:
+        inter_all = inter_per_step
+    ms_per_step = total_ms / args.steps
+    value = inter_all / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers (optb_trace_host): H2D rays + D2H monitor rows ----
+    host = bundle.to_torch(pin=True)
+    host_np = {k: v.numpy() for k, v in host.items()}
+    host_np["length"] = None
+    rs = rays_struct({**{k: None for k in A.RAY_F64}, **host_np})
+    rs.n = n
+    res = A.Result()
+    res.seg_capacity, res.hit_capacity = 0, hit_cap
+    host_out = {}
+    for k in dt.hit_columns:
+        host_out[k] = torch.empty(hit_cap, dtype=dt.t[k].dtype).pin_memory()
+        setattr(res, k, host_out[k].data_ptr())
+    hy = torch.zeros_like(dt.t["hist_y"], device="cpu").pin_memory()
+    hyz = torch.zeros_like(dt.t["hist_yz"], device="cpu").pin_memory()
+    hc = torch.zeros(A.C_COUNT, dtype=torch.int64).pin_memory()
+    res.hist_y, res.hist_yz, res.counters = hy.data_ptr(), hyz.data_ptr(), hc.data_ptr()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        engine.trace_host(dt.scene, rs, dt.prm, res)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        engine.trace_host(dt.scene, rs, dt.prm, res)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    assert int(hc[A.C_INTERACTIONS]) == inter_per_step
+    e2e_value = inter_all * e2e_steps / e2e_s
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = hits_per_step * dt.hit_row_bytes() + hy.numel() * 8 + hyz.numel() * 8 + A.C_COUNT * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    achieved = BYTES_PER_INTERACTION * inter_per_step / (trace_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "trace_kernel", "kernel_ms": trace_ms,
+                "note": "kernel is FP64-pipe bound, not HBM bound: see roofline_fp64 and DESIGN.md"}
+    fp64_peak = engine.fp64_peak_tflops()
+    roofline_fp64 = {"bound": "fp64", "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured in-run (DFMA chain kernel)"}
+    if FLOPS_PER_INTERACTION:
+        af = FLOPS_PER_INTERACTION * inter_per_step / (trace_ms * 1e-3) / 1e12
+        roofline_fp64.update({"achieved": af, "frac": af / fp64_peak})
+    threads = os.cpu_count() or 1
+    cpu_val, cpu_inter, cpu_dt = cpu_arm(flat, args.cpu_rays, threads)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": n, "surfaces": int(flat.n_leaves), "monitors": int(flat.n_monitors),
+                       "interactions_per_step_per_gpu": inter_per_step, "monitor_rows_per_step_per_gpu": hits_per_step,
+                       "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2" % ((h2d + d2h) / 1e9),
+                       "parallelism": f"rays sharded over {world} GPU(s), scene tables replicated"},
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "api": "optb_trace_host (C ABI, pinned host buffers)"},
+            "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"first {args.cpu_rays} rays of the same batch ({cpu_inter} interactions in {cpu_dt:.2f} s), "
+                                       f"oracle/optb_oracle.c with {threads} threads"}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--rays", type=int, default=10_000_000, help="rays per GPU per step")
+    ap.add_argument("--cpu-rays", type=int, default=400_000, help="bounded sample for the in-run CPU baseline")
+    ap.add_argument("--ref-rays", type=int, default=400_000, help="rays per step of the reference arm")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OPTB_ABI_VERSION 3
+#define OPTB_ABI_VERSION 4
 
 /* ---- scene node table ------------------------------------------------------
  * The component tree (OpticalTable.components, groups nested to any depth) is
@@ -166,6 +166,10 @@ typedef struct optb_rays {
   const double* length;     /* Ray.length limit; +inf when None. May be NULL (= all +inf) */
   const uint32_t* flags;    /* OPTB_RF_*. May be NULL (= alive, has q)                */
   const int32_t* family;    /* dense index of Ray._id for interact caps; may be NULL (= root index) */
+  uint32_t broadcast;       /* bit f set: fp64 column f (order above, ox = bit 0 ... length = bit 12) holds ONE
+                               value shared by all n rays (a collimated, monochromatic bundle then costs two
+                               columns of host->device traffic instead of thirteen)                          */
+  uint32_t reserved;
 } optb_rays;
 
 /* ---- parameters ------------------------------------------------------------ */
@@ -205,7 +209,8 @@ typedef struct optb_result {
   uint32_t* seg_root;
   uint32_t* seg_pop;
   int32_t* seg_leaf;       /* dense leaf index that ended the segment; -1 = escaped  */
-  /* monitor hits */
+  /* monitor hits. hit_monitor is required when record_hits == 1; every other hit_* column may be NULL
+   * (not wanted by the caller: it is then neither written nor copied back)                        */
   int32_t* hit_monitor;
   uint32_t* hit_root;
   uint32_t* hit_pop;

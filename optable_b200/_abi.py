@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes and constants against the compiled library."""
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # geometry kinds
 G_GROUP, G_CIRCLE, G_RECT, G_SPHERE, G_ASPHERE, G_CYL, G_POLY2D, G_POLY3D, G_CSG = range(9)
@@ -43,7 +43,8 @@ RAY_F64 = ("ox", "oy", "oz", "dx", "dy", "dz", "intensity", "wavelength", "q_re"
 
 
 class Rays(C.Structure):
-    _fields_ = [("n", C.c_int64)] + [(k, _vp) for k in RAY_F64] + [("flags", _vp), ("family", _vp)]
+    _fields_ = ([("n", C.c_int64)] + [(k, _vp) for k in RAY_F64] + [("flags", _vp), ("family", _vp)]
+                + [("broadcast", C.c_uint32), ("reserved", C.c_uint32)])
 
 
 class Params(C.Structure):

@@ -151,10 +151,13 @@ class Engine:
     @staticmethod
     def _rays_struct(t, n=None):
         s = A.Rays()
-        s.n = int(t["ox"].numel() if n is None else n)
-        for k in A.RAY_F64:
+        s.n = int(max(t[k].numel() for k in A.RAY_F64 if t.get(k) is not None) if n is None else n)
+        s.broadcast = 0
+        for bit, k in enumerate(A.RAY_F64):
             v = t.get(k)
             setattr(s, k, None if v is None else v.data_ptr())
+            if v is not None and v.numel() == 1 and s.n != 1:
+                s.broadcast |= 1 << bit
         for k in ("flags", "family"):
             v = t.get(k)
             setattr(s, k, None if v is None else v.data_ptr())
@@ -196,12 +199,12 @@ class Engine:
         """Enqueue optb_trace on tensors already resident on the device. Asynchronous for scenes that cannot
         split rays; returns after the last generation otherwise."""
         torch = self.torch
-        n = int(rays_t["ox"].numel())
+        rs = self._rays_struct(rays_t)
+        n = int(rs.n)
         splitting = scene.flat.max_children > 1 or params.chain_len > 0
         live = 0 if not splitting else int(max_live if max_live is not None else max(4 * n, 1024))
         nbytes = lib().optb_workspace_bytes(scene._h, n, live)
         ws = self._ws(nbytes)
-        rs = self._rays_struct(rays_t)
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         self._check(lib().optb_trace(self._ctx, scene._h, C.byref(rs), C.byref(params), C.byref(result),
                                      ws.data_ptr(), int(ws.numel()), C.c_void_p(st)))

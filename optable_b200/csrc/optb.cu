@@ -92,11 +92,15 @@ OPTB_DEV unsigned long long warp_alloc(unsigned long long* ctr) {
 OPTB_DEV void load_ray(const TraceArgs& a, long long i, Ray& r, bool& solo, uint32_t& gcount) {
   if (a.gen0) {
     const optb_rays& s = a.in0;
-    r.ox = s.ox[i]; r.oy = s.oy[i]; r.oz = s.oz[i];
-    r.dx = s.dx[i]; r.dy = s.dy[i]; r.dz = s.dz[i];
-    r.I = s.intensity[i]; r.wl = s.wavelength[i]; r.qre = s.q_re[i]; r.qim = s.q_im[i];
-    r.pl = s.pathlength[i]; r.n = s.n_medium[i];
-    r.len = s.length ? s.length[i] : INFINITY;
+    const uint32_t bc = s.broadcast;
+#define OPTB_COL(ptr, bit) ((ptr)[((bc >> (bit)) & 1u) ? 0 : i])
+    r.ox = OPTB_COL(s.ox, 0); r.oy = OPTB_COL(s.oy, 1); r.oz = OPTB_COL(s.oz, 2);
+    r.dx = OPTB_COL(s.dx, 3); r.dy = OPTB_COL(s.dy, 4); r.dz = OPTB_COL(s.dz, 5);
+    r.I = OPTB_COL(s.intensity, 6); r.wl = OPTB_COL(s.wavelength, 7);
+    r.qre = OPTB_COL(s.q_re, 8); r.qim = OPTB_COL(s.q_im, 9);
+    r.pl = OPTB_COL(s.pathlength, 10); r.n = OPTB_COL(s.n_medium, 11);
+    r.len = s.length ? OPTB_COL(s.length, 12) : INFINITY;
+#undef OPTB_COL
     r.flags = s.flags ? s.flags[i] : (OPTB_RF_ALIVE | OPTB_RF_HASQ);
     r.root = (uint32_t)i; r.pop = 0;
     r.family = s.family ? s.family[i] : (int32_t)i;
@@ -169,11 +173,19 @@ OPTB_DEV void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& r
       unsigned long long j = warp_alloc(&a.counters[OPTB_C_HITS]);
       if (j < (unsigned long long)a.out.hit_capacity) {
         const optb_result& o = a.out;
-        o.hit_monitor[j] = m; o.hit_root[j] = r.root; o.hit_pop[j] = r.pop;
-        o.hit_px[j] = Px; o.hit_py[j] = Py; o.hit_pz[j] = Pz;
-        o.hit_intensity[j] = r.I; o.hit_t[j] = t;
-        o.hit_dx[j] = r.dx; o.hit_dy[j] = r.dy; o.hit_dz[j] = r.dz;
-        o.hit_q_re[j] = r.qre; o.hit_q_im[j] = r.qim;
+        o.hit_monitor[j] = m;
+        if (o.hit_root) o.hit_root[j] = r.root;
+        if (o.hit_pop) o.hit_pop[j] = r.pop;
+        if (o.hit_px) o.hit_px[j] = Px;
+        if (o.hit_py) o.hit_py[j] = Py;
+        if (o.hit_pz) o.hit_pz[j] = Pz;
+        if (o.hit_intensity) o.hit_intensity[j] = r.I;
+        if (o.hit_t) o.hit_t[j] = t;
+        if (o.hit_dx) o.hit_dx[j] = r.dx;
+        if (o.hit_dy) o.hit_dy[j] = r.dy;
+        if (o.hit_dz) o.hit_dz[j] = r.dz;
+        if (o.hit_q_re) o.hit_q_re[j] = r.qre;
+        if (o.hit_q_im) o.hit_q_im[j] = r.qim;
       } else {
         atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_HIT_OVERFLOW);
       }
@@ -639,6 +651,7 @@ extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_ray
   cudaSetDevice(ctx->device);
   if (!out->counters) return fail(ctx, -7, "result.counters is required");
   if (rays->n >= 0xffffffffll) return fail(ctx, -7, "at most 2^32-1 rays per call");
+  if (prm->record_hits && out->hit_capacity > 0 && !out->hit_monitor) return fail(ctx, -7, "record_hits needs hit_monitor");
   if (scene->n_caps > 0 && (!out->cap_counts || prm->n_families < 1)) return fail(ctx, -7, "scene has interact caps: cap_counts/n_families required");
   const bool split = needs_wavefront(scene, prm);
   WsLayout L = ws_layout(rays->n, 0, false);
@@ -755,9 +768,10 @@ extern "C" int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const opt
   const double** dst_f = &dr.ox;
   for (int f = 0; f < kRayF64; f++) {
     if (!src_f[f]) { dst_f[f] = nullptr; continue; }
-    void* d = ac.take((size_t)n * 8);
+    const size_t rows = ((rays->broadcast >> f) & 1u) ? 1 : (size_t)n;
+    void* d = ac.take(rows * 8);
     if (!d) return fail(ctx, -9, "arena sizing");
-    CK(cudaMemcpyAsync(d, src_f[f], (size_t)n * 8, cudaMemcpyHostToDevice, st), "H2D rays");
+    CK(cudaMemcpyAsync(d, src_f[f], rows * 8, cudaMemcpyHostToDevice, st), "H2D rays");
     dst_f[f] = (const double*)d;
   }
   if (rays->flags) { void* d = ac.take((size_t)n * 4); CK(cudaMemcpyAsync(d, rays->flags, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D flags"); dr.flags = (const uint32_t*)d; }

@@ -373,10 +373,13 @@ def pack_rays(rays):
 def rays_struct(arrs, n=None) -> A.Rays:
     """ctypes view over a dict of numpy arrays (host pointers)."""
     s = A.Rays()
-    s.n = int(n if n is not None else len(arrs["ox"]))
-    for k in A.RAY_F64:
+    s.n = int(n if n is not None else max(len(arrs[k]) for k in A.RAY_F64 if arrs.get(k) is not None))
+    s.broadcast = 0
+    for bit, k in enumerate(A.RAY_F64):
         a = arrs.get(k)
         setattr(s, k, None if a is None else a.ctypes.data)
+        if a is not None and len(a) == 1 and s.n != 1:
+            s.broadcast |= 1 << bit
     for k in ("flags", "family"):
         a = arrs.get(k)
         setattr(s, k, None if a is None else a.ctypes.data)

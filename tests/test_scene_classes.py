@@ -1,0 +1,62 @@
+"""CPU: optable_b200's own scene classes describe the same scenes as the reference's constructors.
+
+Every fixture scene of tests/scenes.py is built with `ns = optable_b200`, flattened, and compared with the tables
+stored in tests/golden/ (which came from the reference's classes): integer columns exact, floats to 1e-12."""
+import numpy as np
+import pytest
+
+import optable_b200 as ob
+from optable_b200.flatten import FlatScene, pack_rays, trace_cap
+from tests import golden_io, scenes
+
+
+@pytest.mark.parametrize("name", golden_io.names())
+def test_flattened_tables_match_reference_classes(name):
+    want_flat, want_rays, want_params, _ = golden_io.load(name)
+    sc = scenes.REGISTRY[name](ob)
+    flat = FlatScene(sc.components, sc.monitors)
+    np.testing.assert_array_equal(flat.node_i, want_flat.node_i)
+    np.testing.assert_allclose(flat.node_f, want_flat.node_f, rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(flat.mat_kind, want_flat.mat_kind)
+    np.testing.assert_allclose(flat.mat_f, want_flat.mat_f, rtol=1e-15, atol=0)
+    np.testing.assert_allclose(flat.mon_f, want_flat.mon_f, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(flat.aux, want_flat.aux, rtol=1e-12, atol=1e-12)
+    assert flat.max_children == want_flat.max_children
+    arrs, fam_ids, unit = pack_rays(sc.rays)
+    for k, v in want_rays.items():
+        if k == "family":
+            np.testing.assert_array_equal(arrs[k], v)
+        elif arrs[k].dtype.kind == "f":
+            np.testing.assert_allclose(arrs[k], v, rtol=1e-13, atol=1e-15)
+        else:
+            np.testing.assert_array_equal(arrs[k], v)
+    assert trace_cap(sc.limit) == want_params["max_trace_num"]
+    assert unit == want_params["unit"] and len(fam_ids) == want_params["n_families"]
+
+
+def test_pose_verbs():
+    m = ob.Mirror([1, 2, 3]).RotZ(0.3).TX(1).RotYAroundLocal([0, 0, 1], 0.2)
+    assert np.allclose(m.transform_matrix @ m.transform_matrix.T, np.eye(3), atol=1e-14)
+    g = ob.ComponentGroup([0, 0, 0])
+    g.add_components([ob.Mirror([1, 0, 0]), ob.Lens([2, 0, 0], focal_length=3)])
+    g.RotZ(np.pi / 2)
+    assert np.allclose(g.components[0].origin, [0, 1, 0], atol=1e-14)
+    g.TX(1)
+    assert np.allclose(g.components[1].origin, [1, 2, 0], atol=1e-14)
+    r = ob.Ray([0, 0, 0], [2, 0, 0], wavelength=780e-7, w0=61e-4)
+    assert np.allclose(r.direction, [1, 0, 0]) and r.qo.imag > 0 and r.n == 1.0
+    r2 = r.Propagate(-2)
+    assert r2._id == r._id and r2.qo.real == -2
+
+
+def test_error_behaviour_matches_reference():
+    with pytest.raises(TypeError):
+        ob.Sphere(1.0)  # height=None crashes in the reference too (surfaces.py:292)
+    with pytest.raises(ValueError):
+        ob.Polygon([[0, 0], [1, 1]])
+    from optable_b200.flatten import FlattenError
+
+    with pytest.raises(FlattenError):
+        FlatScene([ob.BaseRefraciveSurface([0, 0, 0], n1=1, n2=1.5)])  # bare Plane has no boundary
+    with pytest.raises(FlattenError):
+        FlatScene([ob.CircleRefractive([0, 0, 0], n1=ob.Material("x", lambda wl: 1.5), n2=1)])
