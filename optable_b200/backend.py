@@ -14,7 +14,7 @@ import numpy as np
 from . import _abi as A
 from .flatten import FlatScene
 
-_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboptb.so")
+_SO = os.environ.get("OPTB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboptb.so")
 _lib = None
 
 

@@ -23,6 +23,9 @@ using namespace optb;
 
 namespace {
 
+#ifndef OPTB_MIN_BLOCKS
+#define OPTB_MIN_BLOCKS 4
+#endif
 constexpr int kBlock = 128;
 constexpr int kTile = 2048;  // children-scan tile (entries per block)
 constexpr int kScanBlock = 256;
@@ -202,12 +205,16 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   if (!(ray.flags & OPTB_RF_ALIVE)) return;  // optical_component.py:349-350
   int i = 0;
   const int n = sv.n_nodes;
+  // reciprocals of the lab direction, shared by every box test of this pop (solver.py:27-36)
+  const double o3[3] = {ray.ox, ray.oy, ray.oz};
+  double inv[3]; bool par[3];
+  par[0] = fabs(ray.dx) <= 1e-8; par[1] = fabs(ray.dy) <= 1e-8; par[2] = fabs(ray.dz) <= 1e-8;
+  inv[0] = 1.0 / ray.dx; inv[1] = 1.0 / ray.dy; inv[2] = 1.0 / ray.dz;
   while (i < n) {
     const int32_t* ni = sv.ni + i * OPTB_NI_STRIDE;
     const double* nf = sv.nf + i * OPTB_NF_STRIDE;
     if (ni[OPTB_NI_AABB]) {
-      double t1, t2;
-      if (!slab(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, nf + OPTB_NF_AABB, t1, t2)) { i = ni[OPTB_NI_SKIP]; continue; }
+      if (!slab_pre(o3, inv, par, nf + OPTB_NF_AABB)) { i = ni[OPTB_NI_SKIP]; continue; }
     }
     if (ni[OPTB_NI_GEOM] == OPTB_G_GROUP) { i++; continue; }
     double ox, oy, oz, dx, dy, dz;
@@ -233,7 +240,7 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kBlock) trace_kernel(const __grid_constant__ TraceArgs a) {
+__global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   const unsigned char* base = a.blob;

@@ -71,6 +71,24 @@ OPTB_DEV bool slab(double ox, double oy, double oz, double dx, double dy, double
   return (t2 + 1e-12 >= t1) && (t2 >= 0.0);
 }
 
+// Same test with the reciprocals of the lab direction hoisted out of the node loop (one ray, many boxes).
+// inv[ax] is 1/d[ax]; par[ax] marks the np.isclose(d, 0) axes.
+OPTB_DEV bool slab_pre(const double* o, const double* inv, const bool* par, const double* __restrict__ bb) {
+  double t1 = 0.0, t2 = INFINITY;
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    double bmin = bb[2 * ax], bmax = bb[2 * ax + 1];
+    if (par[ax]) {
+      if (o[ax] < bmin || o[ax] > bmax) { t1 = 1.0; t2 = 0.0; }
+    } else {
+      double ta = (bmin - o[ax]) * inv[ax], tb = (bmax - o[ax]) * inv[ax];
+      t1 = fmax(t1, fmin(ta, tb));
+      t2 = fmin(t2, fmax(ta, tb));
+    }
+  }
+  return (t2 + 1e-12 >= t1) && (t2 >= 0.0);
+}
+
 // ---- ASphere profile (component_group.py:1065-1107) ----
 // The reference differentiates this profile numerically (h = 1e-4 radius, surfaces.py:351-369); the second
 // difference amplifies every rounding of f by ~1e8, so the operation order of the Python closure is kept
@@ -138,13 +156,34 @@ OPTB_DEV bool curved_within(const SceneView& sv, int g, const int32_t* __restric
   return poly_within(sv.aux + ni[OPTB_NI_AUX], Px, Py, Pz);  // POLY3D
 }
 
-// scipy brentq restated (xtol 2e-12, rtol 4 eps, maxiter 100) for the asphere profile
+// ASphere.f along a local ray, for the sign scan and the root solve (surfaces.py:375-378), in a division-free
+// form with the same zeros and the same sign: with s = sqrt(1 - k1 r^2),
+//   f = Px + r^2 / (R (1 + s)) + poly(r^2)   <=>   g = sign(R) * ((Px + poly) * R * (1 + s) + r^2) = f * |R| (1 + s)
+// and |R| (1 + s) > 0. The sag only depends on r^2, so no square root is needed for r either. Constants are
+// folded once per intersection. (The bit-exact form f_asphere() above is reserved for the finite-difference
+// normal / curvature, where the reference's own rounding matters.)
 struct AsphF {
-  int form; const double* c;
+  int form;
+  double k1, R, sgn, a4, a6, a8;  // parametric: k1 = (1+kappa)/R^2 ; exact: k1 = (n+1)/((n-1) EFL^2), R = EFL/(n+1)
   double ox, oy, oz, dx, dy, dz;
+  OPTB_DEV AsphF(int form_, const double* __restrict__ c, double ox_, double oy_, double oz_, double dx_, double dy_, double dz_)
+      : form(form_), ox(ox_), oy(oy_), oz(oz_), dx(dx_), dy(dy_), dz(dz_) {
+    if (form == OPTB_ASPH_PARAMETRIC) {
+      R = c[0]; k1 = (1.0 + c[1]) / (R * R); a4 = c[2]; a6 = c[3]; a8 = c[4];
+      sgn = R < 0 ? -1.0 : 1.0;
+    } else {
+      k1 = (c[1] + 1.0) / ((c[1] - 1.0) * c[0] * c[0]); R = c[0] / (c[1] + 1.0); a4 = a6 = a8 = 0.0; sgn = 1.0;
+    }
+  }
   OPTB_DEV double operator()(double t) const {
     double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
-    return Px + f_asphere(form, c, sqrt(Py * Py + Pz * Pz));  // ASphere.f surfaces.py:375-378
+    double r2 = fma(Py, Py, Pz * Pz);
+    if (form == OPTB_ASPH_PARAMETRIC) {
+      double s = sqrt(fma(-k1, r2, 1.0));
+      double lin = fma(r2 * r2, fma(r2, fma(r2, a8, a6), a4), Px);  // Px + a4 r^4 + a6 r^6 + a8 r^8
+      return sgn * fma(lin * R, 1.0 + s, r2);
+    }
+    return fma(R, sqrt(fma(k1, r2, 1.0)) - 1.0, Px);
   }
 };
 
@@ -235,28 +274,49 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
   const double a = t1 - 1e-9, b = t2 + 1e-9;
   const double step = (b - a) / 9.0;
   // roots found by the sign scan, ascending in t (sub-intervals are visited in order)
-  double r0 = -1.0, r1 = -1.0;  // at most two admissible roots are ever needed before the boundary test
-  int nroot = 0;
   if (g == OPTB_G_ASPHERE) {
-    AsphF f{ni[OPTB_NI_AUX], p + 1, ox, oy, oz, dx, dy, dz};
-    double ta = a, fa = f(a);
-    for (int i = 1; i < 10; i++) {
-      double tb = sample_t(i, a, b, step), fb = f(tb);
-      if (fa * fb < 0) {
-        double r = brentq(f, ta, tb, fa, fb);
-        if (r >= 1e-9 && r <= len) {  // t >= 0 and |t| >= EPS and t <= length
-          // first admissible root inside the aperture wins; later ones only matter if this one fails
+    // Scan first, solve after: every lane walks the 10 samples in lock-step and leaves the inner loop at its
+    // own sign change; the (expensive) root solve then runs once for the whole warp instead of once per
+    // sub-interval.
+    const AsphF f(ni[OPTB_NI_AUX], p + 1, ox, oy, oz, dx, dy, dz);
+    const bool asc = (b >= a);
+    double ta = a, fa = f(a), best = -1.0;
+    int i = 1;
+    while (i < 10) {
+      double tb = ta, fb = fa;
+      bool sc = false;
+      for (; i < 10; i++) {
+        tb = sample_t(i, a, b, step); fb = f(tb);
+        if (fa * fb < 0) { sc = true; break; }
+        ta = tb; fa = fb;
+      }
+      if (!sc) break;
+      bool solve = true;
+      double lo = ta, flo = fa;
+      if (asc) {
+        if (tb <= 1e-9 || ta > len) solve = false;  // every root in here fails t >= EPS (or t <= length)
+        else if (ta < 1e-9) {
+          // The sub-interval straddles the admissibility threshold (the usual case right after leaving this
+          // very surface: the root is the self-intersection at t ~ 0). One sample at t = EPS tells on which
+          // side the root lies; below it the reference finds it with brentq and then filters it out.
+          double fe = f(1e-9);
+          if (fa * fe < 0) solve = false;
+          else if (fe * fb < 0) { lo = 1e-9; flo = fe; }
+        }
+      }
+      if (solve) {
+        double r = brentq(f, lo, tb, flo, fb);
+        if (r >= 1e-9 && r <= len) {
           double Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
-          if (sqrt(Py * Py + Pz * Pz) <= p[0] + 1e-12) {
-            if (b >= a) return r;  // ascending scan: this is the smallest admissible root
-            if (nroot == 0 || r < r0) r0 = r;
-            nroot = 1;
+          if (sqrt(fma(Py, Py, Pz * Pz)) <= p[0] + 1e-12) {   // ASphere.within_boundary
+            if (asc) return r;   // sub-intervals ascend: the first admissible root is the smallest
+            if (best < 0 || r < best) best = r;
           }
         }
       }
-      ta = tb; fa = fb;
+      ta = tb; fa = fb; i++;
     }
-    return nroot ? r0 : -1.0;
+    return best;
   }
   // Quadratic / linear surfaces: g(t) has the sign of Surface.f(o + t d); closed-form roots.
   double A, B, Cc;  // g(t) = A t^2 + 2 B t + C
