@@ -131,7 +131,7 @@ OPTB_DEV void store_child(const RayBuf& c, long long j, const Ray& parent, const
 }
 
 // One pop's dead segment: append to the segment log and test it against every monitor (monitor.py:183-193).
-OPTB_DEV void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& r, double seg_len, uint32_t seg_flags,
+OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& r, double seg_len, uint32_t seg_flags,
                            int leaf, unsigned int* s_hist, unsigned long long& n_hits_local) {
   if (a.rec_seg) {
     unsigned long long j = warp_alloc(&a.counters[OPTB_C_SEGMENTS]);
@@ -198,45 +198,72 @@ OPTB_DEV void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& r
   }
 }
 
-// Closest hit over the flattened tree (optical_table.py:119-123 + component_group.py:93-122).
+// Closest hit over the flattened tree (optical_table.py:119-123 + component_group.py:93-122): smallest t, ties to
+// the smallest pre-order index. Leaves are visited in pre-order except that aspheres (a 10-sample scan plus an
+// iterative root solve each) are parked and tested last, when the closest cheap hit is known: a parked asphere
+// whose bracket starts beyond that hit is dismissed without evaluating its profile once. The (t, index) ordering
+// makes the result independent of the visiting order.
+struct HitSearch {
+  const TraceArgs& a; const SceneView& sv; const Ray& ray; bool solo;
+  double best_t; int best_node; unsigned long long& tests;
+
+  OPTB_DEV void test_leaf(int i, const int32_t* __restrict__ ni, const double* __restrict__ nf) {
+    double ox, oy, oz, dx, dy, dz;
+    to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);
+    tests++;
+    const int slot = ni[OPTB_NI_CAPSLOT];
+    // a capped surface counts every geometric hit, closest or not (optical_component.py:359-362): no early exit
+    double t = intersect_leaf(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len, slot >= 0 ? INFINITY : best_t);
+    if (!(t >= 0.0)) return;
+    if (slot >= 0) {  // should_interact / increase_interact_count :136-149
+      int32_t* cnt = a.out.cap_counts + (long long)slot * a.n_families + ray.family;
+      int old = atomicAdd(cnt, 1);
+      if (!((double)old < nf[OPTB_NF_CAPMAX])) {
+        atomicSub(cnt, 1);
+        if (!solo || a.fam_shared) atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_CAP_ORDER);
+        return;
+      }
+    }
+    if (t < best_t || (t == best_t && i < best_node)) { best_t = t; best_node = i; }
+  }
+};
+
 OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
                           double& best_t, int& best_node, unsigned long long& tests) {
   best_t = INFINITY; best_node = -1;
   if (!(ray.flags & OPTB_RF_ALIVE)) return;  // optical_component.py:349-350
+  HitSearch hs{a, sv, ray, solo, INFINITY, -1, tests};
+  constexpr int kPark = 4;
+  int parked[kPark];
+  int n_parked = 0;
   int i = 0;
   const int n = sv.n_nodes;
-  // reciprocals of the lab direction, shared by every box test of this pop (solver.py:27-36)
-  const double o3[3] = {ray.ox, ray.oy, ray.oz};
-  double inv[3]; bool par[3];
-  par[0] = fabs(ray.dx) <= 1e-8; par[1] = fabs(ray.dy) <= 1e-8; par[2] = fabs(ray.dz) <= 1e-8;
-  inv[0] = 1.0 / ray.dx; inv[1] = 1.0 / ray.dy; inv[2] = 1.0 / ray.dz;
+  const BoxRay br(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz);
   while (i < n) {
     const int32_t* ni = sv.ni + i * OPTB_NI_STRIDE;
     const double* nf = sv.nf + i * OPTB_NF_STRIDE;
     if (ni[OPTB_NI_AABB]) {
-      if (!slab_pre(o3, inv, par, nf + OPTB_NF_AABB)) { i = ni[OPTB_NI_SKIP]; continue; }
+      if (!slab_hit(br, nf + OPTB_NF_AABB)) { i = ni[OPTB_NI_SKIP]; continue; }
     }
-    if (ni[OPTB_NI_GEOM] == OPTB_G_GROUP) { i++; continue; }
-    double ox, oy, oz, dx, dy, dz;
-    to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);
-    tests++;
-    double t = intersect_leaf(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len);
-    if (t >= 0.0) {
-      bool ok = true;
-      int slot = ni[OPTB_NI_CAPSLOT];
-      if (slot >= 0) {  // should_interact / increase_interact_count :136-149, 359-362
-        int32_t* cnt = a.out.cap_counts + (long long)slot * a.n_families + ray.family;
-        int old = atomicAdd(cnt, 1);
-        if (!((double)old < nf[OPTB_NF_CAPMAX])) {
-          atomicSub(cnt, 1);
-          ok = false;
-          if (!solo || a.fam_shared) atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_CAP_ORDER);
-        }
-      }
-      if (ok && t < best_t) { best_t = t; best_node = i; }
+    const int g = ni[OPTB_NI_GEOM];
+    if (g == OPTB_G_GROUP) { i++; continue; }
+    if (g == OPTB_G_ASPHERE && n_parked < kPark) {
+#pragma unroll
+      for (int k = 0; k < kPark; k++) if (k == n_parked) parked[k] = i;
+      n_parked++;
+    } else {
+      hs.test_leaf(i, ni, nf);
     }
     i++;
   }
+#pragma unroll
+  for (int k = 0; k < kPark; k++) {
+    if (k < n_parked) {
+      const int j = parked[k];
+      hs.test_leaf(j, sv.ni + j * OPTB_NI_STRIDE, sv.nf + j * OPTB_NF_STRIDE);
+    }
+  }
+  best_t = hs.best_t; best_node = hs.best_node;
 }
 
 template <bool SMEM>
