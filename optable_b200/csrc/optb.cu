@@ -132,7 +132,7 @@ OPTB_DEV void store_child(const RayBuf& c, long long j, const Ray& parent, const
 
 // One pop's dead segment: append to the segment log and test it against every monitor (monitor.py:183-193).
 OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& r, double seg_len, uint32_t seg_flags,
-                           int leaf, unsigned int* s_hist, unsigned long long& n_hits_local) {
+                           int leaf, unsigned int* s_hist, unsigned int& n_hits_local) {
   if (a.rec_seg) {
     unsigned long long j = warp_alloc(&a.counters[OPTB_C_SEGMENTS]);
     if (j < (unsigned long long)a.out.seg_capacity) {
@@ -205,7 +205,7 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
 // makes the result independent of the visiting order.
 struct HitSearch {
   const TraceArgs& a; const SceneView& sv; const Ray& ray; bool solo;
-  double best_t; int best_node; unsigned long long& tests;
+  double best_t; int best_node; unsigned int& tests;
 
   OPTB_DEV void test_leaf(int i, const int32_t* __restrict__ ni, const double* __restrict__ nf) {
     double ox, oy, oz, dx, dy, dz;
@@ -229,39 +229,42 @@ struct HitSearch {
 };
 
 OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
-                          double& best_t, int& best_node, unsigned long long& tests) {
+                          double& best_t, int& best_node, unsigned int& tests) {
   best_t = INFINITY; best_node = -1;
   if (!(ray.flags & OPTB_RF_ALIVE)) return;  // optical_component.py:349-350
   HitSearch hs{a, sv, ray, solo, INFINITY, -1, tests};
   constexpr int kPark = 4;
   int parked[kPark];
-  int n_parked = 0;
+  int n_parked = 0, n_done = 0;
   int i = 0;
   const int n = sv.n_nodes;
   const BoxRay br(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz);
-  while (i < n) {
-    const int32_t* ni = sv.ni + i * OPTB_NI_STRIDE;
-    const double* nf = sv.nf + i * OPTB_NF_STRIDE;
-    if (ni[OPTB_NI_AABB]) {
-      if (!slab_hit(br, nf + OPTB_NF_AABB)) { i = ni[OPTB_NI_SKIP]; continue; }
-    }
-    const int g = ni[OPTB_NI_GEOM];
-    if (g == OPTB_G_GROUP) { i++; continue; }
-    if (g == OPTB_G_ASPHERE && n_parked < kPark) {
+  // One loop, one test_leaf call site (the leaf test is ~2/3 of the kernel's code; inlining it twice thrashes the
+  // instruction cache): first the pre-order walk, then the parked aspheres.
+  while (true) {
+    int leaf = -1;
+    while (i < n) {
+      const int32_t* ni = sv.ni + i * OPTB_NI_STRIDE;
+      if (ni[OPTB_NI_AABB] && !slab_hit(br, sv.nf + i * OPTB_NF_STRIDE + OPTB_NF_AABB)) { i = ni[OPTB_NI_SKIP]; continue; }
+      const int g = ni[OPTB_NI_GEOM];
+      const int cur = i++;
+      if (g == OPTB_G_GROUP) continue;
+      if (g == OPTB_G_ASPHERE && n_parked < kPark) {
 #pragma unroll
-      for (int k = 0; k < kPark; k++) if (k == n_parked) parked[k] = i;
-      n_parked++;
-    } else {
-      hs.test_leaf(i, ni, nf);
+        for (int k = 0; k < kPark; k++) if (k == n_parked) parked[k] = cur;
+        n_parked++;
+        continue;
+      }
+      leaf = cur;
+      break;
     }
-    i++;
-  }
+    if (leaf < 0) {
+      if (n_done >= n_parked) break;
 #pragma unroll
-  for (int k = 0; k < kPark; k++) {
-    if (k < n_parked) {
-      const int j = parked[k];
-      hs.test_leaf(j, sv.ni + j * OPTB_NI_STRIDE, sv.nf + j * OPTB_NF_STRIDE);
+      for (int k = 0; k < kPark; k++) if (k == n_done) leaf = parked[k];
+      n_done++;
     }
+    hs.test_leaf(leaf, sv.ni + leaf * OPTB_NI_STRIDE, sv.nf + leaf * OPTB_NF_STRIDE);
   }
   best_t = hs.best_t; best_node = hs.best_node;
 }
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
 
   const long long n_in = a.n_in_dev ? (long long)*a.n_in_dev : a.n_in;
   const int lane = threadIdx.x & 31;
-  unsigned long long c_pops = 0, c_inter = 0, c_tests = 0, c_drop = 0, c_hits = 0;
+  unsigned int c_pops = 0, c_inter = 0, c_tests = 0, c_drop = 0, c_hits = 0;  // per thread; widened when reduced
 
   while (true) {
     unsigned int chunk = 0;
@@ -324,14 +327,14 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
       double t; int node;
       closest_hit(a, sv, ray, solo, t, node, c_tests);
       c_pops++;
-      if (node < 0) {  // optical_table.py:132-134: the ray itself, untouched
-        emit_segment(a, sv, ray, ray.len, ray.flags, -1, s_hist, c_hits);
-        nch = 0;
-        break;
-      }
-      const int32_t* ni = sv.ni + node * OPTB_NI_STRIDE;
-      const double* nf = sv.nf + node * OPTB_NF_STRIDE;
-      emit_segment(a, sv, ray, t, ray.flags & ~OPTB_RF_ALIVE, ni[OPTB_NI_LEAF], s_hist, c_hits);
+      // the pop's dead segment: the ray itself when nothing was hit (optical_table.py:132-134), else the
+      // truncated copy with length = t, alive = False (optical_component.py:364)
+      const bool hit = node >= 0;
+      const int32_t* ni = sv.ni + (hit ? node : 0) * OPTB_NI_STRIDE;
+      const double* nf = sv.nf + (hit ? node : 0) * OPTB_NF_STRIDE;
+      emit_segment(a, sv, ray, hit ? t : ray.len, hit ? (ray.flags & ~OPTB_RF_ALIVE) : ray.flags,
+                   hit ? ni[OPTB_NI_LEAF] : -1, s_hist, c_hits);
+      if (!hit) { nch = 0; break; }
       c_inter++;
       double ox, oy, oz, dx, dy, dz;
       to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);

@@ -238,3 +238,25 @@ REGISTRY = {
     "misc_components": misc_components,
     "mma_small": mma_small,
 }
+
+
+# ---- array-level ray batches for the scale tests (no Python Ray objects) ---------------------------------------
+def ray_arrays(n, origin, spread_pos, direction, spread_dir, wavelengths=(780e-7,), w0=61e-4, seed=SEED + 100):
+    """n rays: origin + U(-spread_pos, spread_pos) per axis, direction + N(0, spread_dir) (normalised), wavelengths
+    cycled; Gaussian q from w0 (0 = no q). Returns the dict layout of optable_b200.flatten.pack_rays."""
+    rng = np.random.default_rng(seed)
+    o = np.asarray(origin, float) + rng.uniform(-1, 1, (n, 3)) * np.asarray(spread_pos, float)
+    d = np.asarray(direction, float) + rng.standard_normal((n, 3)) * np.asarray(spread_dir, float)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    wl = np.asarray(wavelengths, float)[np.arange(n) % len(wavelengths)]
+    arrs = {"ox": o[:, 0].copy(), "oy": o[:, 1].copy(), "oz": o[:, 2].copy(),
+            "dx": d[:, 0].copy(), "dy": d[:, 1].copy(), "dz": d[:, 2].copy(),
+            "intensity": np.ones(n), "wavelength": wl, "pathlength": np.zeros(n), "n_medium": np.ones(n),
+            "length": np.full(n, np.inf)}
+    if w0:
+        arrs["q_re"], arrs["q_im"] = np.zeros(n), np.pi * w0 ** 2 / wl
+    else:
+        arrs["q_re"], arrs["q_im"] = np.zeros(n), np.zeros(n)
+    arrs["flags"] = np.full(n, 1 | (2 if w0 else 0), dtype=np.uint32)
+    arrs["family"] = np.arange(n, dtype=np.int32)
+    return arrs
