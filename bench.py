@@ -29,7 +29,7 @@ UNIT = "interactions/s"
 WORKLOAD = "c2_4f_telescope"
 BYTES_PER_INTERACTION = 208  # read + write one 104-B ray record per interaction (wavefront form)
 # fp64 flops per interaction of this workload, from the ncu instruction counts of profiles/ 
-FLOPS_PER_INTERACTION = None
+FLOPS_PER_INTERACTION = 1832  # executed (2*DFMA + DMUL + DADD) / interactions, profiles/r1_trace_kernel_summary.md
 
 
 def build_scene():
