@@ -201,8 +201,10 @@ class Engine:
         torch = self.torch
         rs = self._rays_struct(rays_t)
         n = int(rs.n)
-        splitting = scene.flat.max_children > 1 or params.chain_len > 0
+        splitting = scene.flat.max_children > 1 or params.chain_len > 0 or scene.flat.n_capslots > 0
         live = 0 if not splitting else int(max_live if max_live is not None else max(4 * n, 1024))
+        if scene.flat.n_capslots:  # family-serial mode: total FIFO entries over all families
+            live = max(live, min(64 * max(n, 16), n * (int(params.max_trace_num) + 2)))
         nbytes = lib().optb_workspace_bytes(scene._h, n, live)
         ws = self._ws(nbytes)
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream

@@ -59,6 +59,9 @@ struct TraceArgs {
   optb_result out;
   unsigned long long* counters;
   Header* hdr;
+  // family-serial mode (scenes with interact caps): one thread owns one Ray._id family and replays the
+  // reference's sequential order; w is then a per-family FIFO ring of qcap entries
+  const uint32_t* fam_off; uint32_t* fam_roots; uint32_t qcap;
 };
 
 OPTB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,6 +131,17 @@ OPTB_DEV void store_child(const RayBuf& c, long long j, const Ray& parent, const
   c.f[6][j] = ch.I[k]; c.f[7][j] = parent.wl; c.f[8][j] = ch.qre[k]; c.f[9][j] = ch.qim[k];
   c.f[10][j] = ch.pl; c.f[11][j] = ch.nmed[k]; c.f[12][j] = parent.len;
   c.flags[j] = parent.flags; c.root[j] = parent.root; c.pop[j] = pop_base; c.family[j] = parent.family;
+}
+
+OPTB_DEV void ring_put(const RayBuf& w, long long j, const Ray& r) {
+  w.f[0][j] = r.ox; w.f[1][j] = r.oy; w.f[2][j] = r.oz; w.f[3][j] = r.dx; w.f[4][j] = r.dy; w.f[5][j] = r.dz;
+  w.f[6][j] = r.I; w.f[7][j] = r.wl; w.f[8][j] = r.qre; w.f[9][j] = r.qim; w.f[10][j] = r.pl; w.f[11][j] = r.n;
+  w.f[12][j] = r.len; w.flags[j] = r.flags;
+}
+OPTB_DEV void ring_get(const RayBuf& w, long long j, Ray& r) {
+  r.ox = w.f[0][j]; r.oy = w.f[1][j]; r.oz = w.f[2][j]; r.dx = w.f[3][j]; r.dy = w.f[4][j]; r.dz = w.f[5][j];
+  r.I = w.f[6][j]; r.wl = w.f[7][j]; r.qre = w.f[8][j]; r.qim = w.f[9][j]; r.pl = w.f[10][j]; r.n = w.f[11][j];
+  r.len = w.f[12][j]; r.flags = w.flags[j];
 }
 
 // One pop's dead segment: append to the segment log and test it against every monitor (monitor.py:183-193).
@@ -269,7 +283,7 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   best_t = hs.best_t; best_node = hs.best_node;
 }
 
-template <bool SMEM>
+template <bool SMEM, bool SERIAL>
 __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -314,6 +328,53 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
     long long i = (long long)chunk * 32 + lane;
     if ((long long)chunk * 32 >= n_in) break;
     if (i >= n_in) continue;
+
+    if constexpr (SERIAL) {
+      // Work item = one Ray._id family. Its initial rays are traced one after another in input order, each
+      // with the reference's own FIFO loop (optical_table.py:74-147), so interact counts evolve exactly as
+      // in the reference (optical_component.py:136-149, 359-362).
+      const uint32_t lo = a.fam_off[i], hi = a.fam_off[i + 1];
+      for (uint32_t x = lo + 1; x < hi; x++) {  // the scatter is unordered: restore input order
+        uint32_t v = a.fam_roots[x]; uint32_t y = x;
+        while (y > lo && a.fam_roots[y - 1] > v) { a.fam_roots[y] = a.fam_roots[y - 1]; y--; }
+        a.fam_roots[y] = v;
+      }
+      const long long ring = (long long)i * a.qcap;
+      for (uint32_t x = lo; x < hi; x++) {
+        Ray ray; bool solo; uint32_t gcount;
+        const uint32_t root = a.fam_roots[x];
+        load_ray(a, root, ray, solo, gcount);
+        uint32_t head = 0, tail = 0, pops = 0;
+        ring_put(a.w, ring, ray); tail = 1;
+        while ((long long)pops < a.max_trace && head != tail) {
+          ring_get(a.w, ring + head % a.qcap, ray); head++;
+          ray.root = root; ray.family = (int32_t)i; ray.pop = pops++;
+          double t; int node;
+          closest_hit(a, sv, ray, true, t, node, c_tests);
+          c_pops++;
+          const bool hit = node >= 0;
+          const int32_t* ni = sv.ni + (hit ? node : 0) * OPTB_NI_STRIDE;
+          const double* nf = sv.nf + (hit ? node : 0) * OPTB_NF_STRIDE;
+          emit_segment(a, sv, ray, hit ? t : ray.len, hit ? (ray.flags & ~OPTB_RF_ALIVE) : ray.flags,
+                       hit ? ni[OPTB_NI_LEAF] : -1, s_hist, c_hits);
+          if (!hit) continue;
+          c_inter++;
+          double ox, oy, oz, dx, dy, dz;
+          to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);
+          Children ch;
+          interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch);
+          for (int k = 0; k < ch.n; k++) {
+            if (tail - head >= a.qcap) { atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_WORK_OVERFLOW); break; }
+            Ray c = ray;
+            c.ox = ch.ox; c.oy = ch.oy; c.oz = ch.oz; c.dx = ch.dx[k]; c.dy = ch.dy[k]; c.dz = ch.dz[k];
+            c.I = ch.I[k]; c.qre = ch.qre[k]; c.qim = ch.qim[k]; c.pl = ch.pl; c.n = ch.nmed[k];
+            ring_put(a.w, ring + tail % a.qcap, c); tail++;
+          }
+        }
+        c_drop += tail - head;
+      }
+      continue;
+    }
 
     Ray ray; bool solo; uint32_t gcount;
     load_ray(a, i, ray, solo, gcount);
@@ -486,6 +547,19 @@ __global__ void mark_kernel(const uint32_t* __restrict__ root, const Header* hdr
     uint32_t r = root[j];
     if (j == 0 || root[j - 1] != r) gen_first[r] = (uint32_t)j;
     if (j == n - 1 || root[j + 1] != r) gen_last[r] = (uint32_t)j;
+  }
+}
+
+// family -> list of initial rays (CSR) for the family-serial mode
+__global__ void fam_count_kernel(const int32_t* __restrict__ family, long long n, unsigned int* __restrict__ counts) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&counts[family ? family[i] : (int32_t)i], 1u);
+}
+__global__ void fam_scatter_kernel(const int32_t* __restrict__ family, long long n, const unsigned int* __restrict__ off,
+                                   unsigned int* __restrict__ cursor, uint32_t* __restrict__ roots) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int f = family ? family[i] : (int32_t)i;
+    roots[off[f] + atomicAdd(&cursor[f], 1u)] = (uint32_t)i;
   }
 }
 
@@ -672,13 +746,31 @@ RayBuf make_raybuf(unsigned char* base, long long cap) {
   return b;
 }
 bool needs_wavefront(const optb_scene* s, const optb_params* p) { return s->max_children > 1 || p->chain_len > 0; }
+// Interact caps make the result depend on the reference's sequential order as soon as two rays of one family can
+// be in flight: splitting scenes, or several initial rays sharing an `_id` (family column given).
+bool needs_serial(const optb_scene* s, const optb_rays* r) { return s->n_caps > 0 && (s->max_children > 1 || r->family != nullptr); }
+struct SerialLayout { size_t hdr, off, cursor, roots, ring, total; };
+SerialLayout serial_layout(long long n_rays, long long n_fam, long long ring_entries) {
+  SerialLayout L{};
+  size_t o = 0;
+  L.hdr = o; o += align_up(sizeof(Header), 256);
+  L.off = o; o += align_up((size_t)(n_fam + 2) * 4, 256);
+  L.cursor = o; o += align_up((size_t)(n_fam + 1) * 4, 256);
+  L.roots = o; o += align_up((size_t)std::max<long long>(n_rays, 1) * 4, 256);
+  L.ring = o; o += raybuf_bytes(std::max<long long>(ring_entries, 1));
+  L.total = o;
+  return L;
+}
 }  // namespace
 
 extern "C" int64_t optb_workspace_bytes(const optb_scene* scene, int64_t n_rays, int64_t max_live) {
   if (!scene || n_rays < 0) return -1;
   // the caller may later pass chain_len > 0, so always size for the wavefront when asked for max_live > 0
   bool split = scene->max_children > 1 || max_live > 0;
-  return (int64_t)ws_layout(n_rays, std::max<int64_t>(max_live, n_rays), split).total;
+  int64_t need = (int64_t)ws_layout(n_rays, std::max<int64_t>(max_live, n_rays), split).total;
+  if (scene->n_caps > 0)  // family-serial mode: max_live = total FIFO entries over all families
+    need = std::max<int64_t>(need, (int64_t)serial_layout(n_rays, n_rays, std::max<int64_t>(max_live, 8 * n_rays)).total);
+  return need;
 }
 
 extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
@@ -690,10 +782,28 @@ extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_ray
   if (rays->n >= 0xffffffffll) return fail(ctx, -7, "at most 2^32-1 rays per call");
   if (prm->record_hits && out->hit_capacity > 0 && !out->hit_monitor) return fail(ctx, -7, "record_hits needs hit_monitor");
   if (scene->n_caps > 0 && (!out->cap_counts || prm->n_families < 1)) return fail(ctx, -7, "scene has interact caps: cap_counts/n_families required");
-  const bool split = needs_wavefront(scene, prm);
+  const bool serial = needs_serial(scene, rays);
+  const bool split = !serial && needs_wavefront(scene, prm);
   WsLayout L = ws_layout(rays->n, 0, false);
   long long cap = 0;
-  if (split) {
+  SerialLayout SL{};
+  long long n_fam = 0, qcap = 0;
+  if (serial) {
+    n_fam = rays->family ? prm->n_families : rays->n;
+    if (n_fam < 1) return fail(ctx, -7, "n_families must be >= 1");
+    const long long want = std::min<long long>(prm->max_trace_num + 2, 1ll << 20);
+    const size_t fixed = serial_layout(rays->n, n_fam, 1).total;
+    if ((size_t)workspace_bytes <= fixed) return fail(ctx, -8, "workspace too small (see optb_workspace_bytes)");
+    long long lo = 1, hi = std::max<long long>(want, 2) * n_fam;
+    while (lo < hi) {
+      long long mid = lo + (hi - lo + 1) / 2;
+      if ((int64_t)serial_layout(rays->n, n_fam, mid).total <= workspace_bytes) lo = mid; else hi = mid - 1;
+    }
+    qcap = std::min<long long>(lo / n_fam, want);
+    if (qcap < 4) return fail(ctx, -8, "workspace too small for the per-family FIFO (see optb_workspace_bytes)");
+    SL = serial_layout(rays->n, n_fam, qcap * n_fam);
+    L.hdr = SL.hdr;
+  } else if (split) {
     // find the largest wavefront capacity the given workspace supports
     if (workspace_bytes < (int64_t)ws_layout(rays->n, rays->n, true).total) return fail(ctx, -8, "workspace too small (see optb_workspace_bytes)");
     long long lo = rays->n, hi = std::max<long long>(rays->n, 1) * 64;
@@ -738,7 +848,8 @@ extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_ray
     a.gen_last = (uint32_t*)(ws + L.gen_last);
   }
   uint32_t smem = scene->in_smem ? scene->smem_bytes : (a.hist_smem ? scene->smem_bytes : 0);
-  auto kern = scene->in_smem ? trace_kernel<true> : trace_kernel<false>;
+  auto kern = serial ? (scene->in_smem ? trace_kernel<true, true> : trace_kernel<false, true>)
+                     : (scene->in_smem ? trace_kernel<true, false> : trace_kernel<false, false>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
   int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem), "occupancy");
@@ -747,6 +858,27 @@ extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_ray
 
   unsigned long long gens = 0, launches = 0;
   long long n_in = rays->n;
+  if (serial && n_in > 0) {
+    unsigned int* off = (unsigned int*)(ws + SL.off);
+    unsigned int* cursor = (unsigned int*)(ws + SL.cursor);
+    uint32_t* roots = (uint32_t*)(ws + SL.roots);
+    CK(cudaMemsetAsync(off, 0, (size_t)(n_fam + 2) * 4, st), "memset family offsets");
+    CK(cudaMemsetAsync(cursor, 0, (size_t)(n_fam + 1) * 4, st), "memset family cursors");
+    const int g = (int)std::min<long long>(full_grid * 4, (n_in + 255) / 256);
+    fam_count_kernel<<<g, 256, 0, st>>>(rays->family, n_in, off);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(off, (int)(n_fam + 1), hdr, a.counters, 0xffffffffu);  // exclusive, in place
+    fam_scatter_kernel<<<g, 256, 0, st>>>(rays->family, n_in, off, cursor, roots);
+    a.fam_off = off; a.fam_roots = roots; a.qcap = (uint32_t)qcap;
+    a.w = make_raybuf(ws + SL.ring, qcap * n_fam);
+    a.fam_shared = 0;
+    a.n_in = n_fam;
+    if (!rays->family) a.n_families = (int)std::min<long long>(n_fam, 0x7fffffff);
+    void* kargs[] = {(void*)&a};
+    int grid = (int)std::min<long long>(full_grid, (n_fam + kBlock - 1) / kBlock);
+    CK(cudaLaunchKernel((const void*)kern, dim3(grid), dim3(kBlock), kargs, smem, st), "launch trace_kernel (family-serial)");
+    launches += 4; gens = 1;
+    n_in = 0;
+  }
   while (n_in > 0) {
     long long want = (n_in + kBlock - 1) / kBlock;
     int grid = (int)std::min<long long>(full_grid, want);
@@ -784,10 +916,11 @@ extern "C" int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const opt
   if (!ctx || !scene || !rays || !prm || !out) return -1;
   cudaSetDevice(ctx->device);
   const int64_t n = rays->n;
-  const bool split = needs_wavefront(scene, prm);
+  const bool split = needs_wavefront(scene, prm) || needs_serial(scene, rays);
   const int64_t segcap = prm->record_segments ? out->seg_capacity : 0, hitcap = prm->record_hits ? out->hit_capacity : 0;
   const int64_t max_live = split ? std::max<int64_t>(4 * n, 1024) : 0;
-  const int64_t wsb = (int64_t)ws_layout(n, max_live, split).total;
+  const int64_t wsb = needs_serial(scene, rays) ? optb_workspace_bytes(scene, n, 64 * std::max<int64_t>(n, 16))
+                                               : (int64_t)ws_layout(n, max_live, split).total;
   const int nfam = std::max(prm->n_families, 1);
   size_t need = 256 * 64 + (size_t)n * (8 * 13 + 8) + (size_t)segcap * (13 * 8 + 16) + (size_t)hitcap * (10 * 8 + 12) +
                 (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 8 +

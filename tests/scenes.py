@@ -222,6 +222,20 @@ def mma_small(ns):
     return Scene([grp], rays, [mon], limit={"max_trace_num": 120})
 
 
+def caps_binding(ns):
+    """Interact caps that really bind: a TriangularPrism whose faces 2/3 stop interacting after 3 hits
+    per ray id, partial reflections everywhere (splitting), and each ray multiplexed into 6 wavelengths that share
+    its `_id`, so the visible set depends on the reference's sequential order across wavelengths and pops."""
+    L = 6
+    ps = ns.TriangularPrism(origin=[0, 0, 0], width=L, height=L, n1=1, n2=ns.Glass_NBK7(), alpha=np.pi / 4, beta=np.pi / 2,
+                            reflectivity_1=0.3, reflectivity_2=0.5, reflectivity_3=0.4, max_interact_count_2=3,
+                            max_interact_count_3=3)
+    r0 = [ns.Ray([3, y + L / 2, 0.1 * y], [-1, 0.02 * y, 0], wavelength=780e-7, w0=61e-4, id=10 + i)
+          for i, y in enumerate(np.linspace(-2.5, 2.5, 4))]
+    rays = ns.multiplex_rays_in_wavelength(r0, list(np.linspace(450e-7, 900e-7, 6)))
+    return Scene([ps], rays, [ns.Monitor([-3, 0, 0], width=2 * L, height=2 * L)], limit={"max_trace_num": 80})
+
+
 REGISTRY = {
     "gaussian_beam": gaussian_beam,
     "glass_slab": glass_slab,
@@ -237,6 +251,7 @@ REGISTRY = {
     "gaussian_telescope": gaussian_telescope,
     "misc_components": misc_components,
     "mma_small": mma_small,
+    "caps_binding": caps_binding,
 }
 
 

@@ -28,7 +28,7 @@ def _objects_to_arrays(segs, roots):
     return out
 
 
-@pytest.mark.parametrize("name", ["gaussian_beam", "chromatic", "doublet", "prism_refl", "misc_components", "mirror_pair"])
+@pytest.mark.parametrize("name", ["gaussian_beam", "chromatic", "doublet", "prism_refl", "caps_binding", "misc_components", "mirror_pair"])
 def test_ray_tracing_objects_match_reference(name):
     _, _, _, ref = golden_io.load(name)
     sc = scenes.REGISTRY[name](ob)
