@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OPTB_ABI_VERSION 4
+#define OPTB_ABI_VERSION 5
 
 /* ---- scene node table ------------------------------------------------------
  * The component tree (OpticalTable.components, groups nested to any depth) is
@@ -182,7 +182,10 @@ typedef struct optb_params {
   int32_t chain_len;      /* max in-thread pops per launch for a root whose alive set is one ray
                              (0 = unlimited). Scheduling only; results do not depend on it.   */
   int32_t n_families;     /* rows of cap_counts per slot                                */
-  int32_t reserved;
+  int32_t caps_slack;     /* 1: the caller guarantees that no interact cap can bind in this call (every cap >=
+                             initial count + max_trace_num * rays per family). Counts are still kept, but the
+                             scene is traced on the parallel path instead of the family-serial one. If a cap
+                             binds anyway, OPTB_ST_CAP_ORDER is raised.                                  */
 } optb_params;
 
 /* ---- results ---------------------------------------------------------------

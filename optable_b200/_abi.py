@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes and constants against the compiled library."""
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # geometry kinds
 G_GROUP, G_CIRCLE, G_RECT, G_SPHERE, G_ASPHERE, G_CYL, G_POLY2D, G_POLY3D, G_CSG = range(9)
@@ -51,7 +51,7 @@ class Params(C.Structure):
     _fields_ = [
         ("max_trace_num", C.c_int64), ("unit", C.c_double),
         ("record_segments", C.c_int32), ("record_hits", C.c_int32), ("record_hist", C.c_int32),
-        ("chain_len", C.c_int32), ("n_families", C.c_int32), ("reserved", C.c_int32),
+        ("chain_len", C.c_int32), ("n_families", C.c_int32), ("caps_slack", C.c_int32),
     ]
 
 

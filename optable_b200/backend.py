@@ -188,11 +188,11 @@ class Engine:
 
     @staticmethod
     def make_params(max_trace_num=2000, unit=1e-2, record_segments=True, record_hits=True, record_hist=False,
-                    chain_len=0, n_families=1):
+                    chain_len=0, n_families=1, caps_slack=0):
         p = A.Params()
         p.max_trace_num, p.unit = int(max_trace_num), float(unit)
         p.record_segments, p.record_hits, p.record_hist = int(record_segments), int(record_hits), int(record_hist)
-        p.chain_len, p.n_families = int(chain_len), int(n_families)
+        p.chain_len, p.n_families, p.caps_slack = int(chain_len), int(n_families), int(caps_slack)
         return p
 
     def trace_device(self, scene: Scene, rays_t, params: A.Params, result: A.Result, max_live=None, stream=None):
@@ -226,11 +226,15 @@ class Engine:
             n_families = int(arrs["family"].max()) + 1 if n else 1
         rays_t = self.rays_to_device(arrs)
         flat = scene.flat
-        caps0 = None
+        caps0, slack = None, 0
         if flat.n_capslots:
             caps0 = np.zeros((flat.n_capslots, n_families), np.int32) if cap_counts is None else np.array(cap_counts, np.int32)
+            # can any cap bind at all? a family's count grows by at most one per pop of each of its initial rays
+            fam_size = np.bincount(arrs["family"], minlength=n_families).max() if n else 0
+            capmax = flat.node_f[flat.node_i[:, A.NI_CAPSLOT] >= 0, A.NF_CAPMAX].min()
+            slack = int(caps0.max() + int(max_trace_num) * int(fam_size) <= capmax)
         # pass 1: count rows (interact-count side effects go to a scratch table)
-        prm = self.make_params(max_trace_num, unit, False, False, False, chain_len, n_families)
+        prm = self.make_params(max_trace_num, unit, False, False, False, chain_len, n_families, slack)
         res, t = self.alloc_result(scene, 0, 0, n_families, caps0)
         self.trace_device(scene, rays_t, prm, res, max_live)
         cnt = t["counters"].cpu().numpy()
@@ -238,7 +242,7 @@ class Engine:
         nseg = int(cnt[A.C_SEGMENTS]) if record_segments else 0
         nhit = int(cnt[A.C_HITS]) if record_hits else 0
         # pass 2: record
-        prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families)
+        prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families, slack)
         res, t = self.alloc_result(scene, nseg, nhit, n_families, caps0)
         self.trace_device(scene, rays_t, prm, res, max_live)
         torch.cuda.synchronize(self.device)

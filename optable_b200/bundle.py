@@ -114,7 +114,16 @@ class DeviceTrace:
             if k not in hit_columns and k != "hit_monitor":
                 setattr(self.res, k, None)
                 self.t.pop(k)
-        self.prm = engine.make_params(max_trace_num, unit, seg_capacity > 0, hit_capacity > 0, record_hist, chain_len, n_rays)
+        slack = 0
+        if flat.n_capslots:
+            # a bundle ray is its own `_id` family starting from zero counts: a cap can only bind if it is
+            # smaller than the pop budget. Binding caps need Ray objects (OpticalTable.ray_tracing).
+            capmax = flat.node_f[flat.node_i[:, A.NI_CAPSLOT] >= 0, A.NF_CAPMAX].min()
+            if capmax < max_trace_num:
+                raise NotImplementedError("bundle traces need max_interact_count >= max_trace_num on every capped component")
+            slack = 1
+        self.prm = engine.make_params(max_trace_num, unit, seg_capacity > 0, hit_capacity > 0, record_hist, chain_len,
+                                      n_rays, slack)
         self.hit_columns = tuple(k for k in HIT_COLUMNS_ALL if k in self.t)
 
     def run(self, rays_t):
@@ -137,8 +146,6 @@ def trace_bundle(table, bundle: RayBundle, perfomance_limit=None, record_hits=Tr
 
     engine = engine or Engine.get()
     flat = FlatScene(table.components, table.monitors)
-    if flat.n_capslots:
-        raise NotImplementedError("trace_bundle does not support max_interact_count scenes; use ray_tracing")
     cap = int(hit_capacity if hit_capacity is not None else bundle.n * max(flat.n_monitors, 1) * 2) if record_hits else 0
     dt = DeviceTrace(engine, flat, bundle.n, cap, max_trace_num=trace_cap(perfomance_limit), record_hist=record_hist)
     dt.run(bundle.to_torch(device=f"cuda:{engine.device}"))

@@ -748,7 +748,9 @@ RayBuf make_raybuf(unsigned char* base, long long cap) {
 bool needs_wavefront(const optb_scene* s, const optb_params* p) { return s->max_children > 1 || p->chain_len > 0; }
 // Interact caps make the result depend on the reference's sequential order as soon as two rays of one family can
 // be in flight: splitting scenes, or several initial rays sharing an `_id` (family column given).
-bool needs_serial(const optb_scene* s, const optb_rays* r) { return s->n_caps > 0 && (s->max_children > 1 || r->family != nullptr); }
+bool needs_serial(const optb_scene* s, const optb_rays* r, const optb_params* p) {
+  return s->n_caps > 0 && !p->caps_slack && (s->max_children > 1 || r->family != nullptr);
+}
 struct SerialLayout { size_t hdr, off, cursor, roots, ring, total; };
 SerialLayout serial_layout(long long n_rays, long long n_fam, long long ring_entries) {
   SerialLayout L{};
@@ -782,7 +784,7 @@ extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_ray
   if (rays->n >= 0xffffffffll) return fail(ctx, -7, "at most 2^32-1 rays per call");
   if (prm->record_hits && out->hit_capacity > 0 && !out->hit_monitor) return fail(ctx, -7, "record_hits needs hit_monitor");
   if (scene->n_caps > 0 && (!out->cap_counts || prm->n_families < 1)) return fail(ctx, -7, "scene has interact caps: cap_counts/n_families required");
-  const bool serial = needs_serial(scene, rays);
+  const bool serial = needs_serial(scene, rays, prm);
   const bool split = !serial && needs_wavefront(scene, prm);
   WsLayout L = ws_layout(rays->n, 0, false);
   long long cap = 0;
@@ -835,7 +837,7 @@ extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_ray
   a.max_trace = prm->max_trace_num; a.unit = prm->unit;
   a.rec_seg = prm->record_segments; a.rec_hit = prm->record_hits; a.rec_hist = prm->record_hist && scene->n_mons > 0;
   a.chain_len = prm->chain_len; a.n_families = prm->n_families;
-  a.fam_shared = (rays->family != nullptr);
+  a.fam_shared = (rays->family != nullptr) || prm->caps_slack;
   a.hist_smem = a.rec_hist && scene->hist_smem;
   a.out = *out;
   a.counters = (unsigned long long*)out->counters;
@@ -916,10 +918,10 @@ extern "C" int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const opt
   if (!ctx || !scene || !rays || !prm || !out) return -1;
   cudaSetDevice(ctx->device);
   const int64_t n = rays->n;
-  const bool split = needs_wavefront(scene, prm) || needs_serial(scene, rays);
+  const bool split = needs_wavefront(scene, prm) || needs_serial(scene, rays, prm);
   const int64_t segcap = prm->record_segments ? out->seg_capacity : 0, hitcap = prm->record_hits ? out->hit_capacity : 0;
   const int64_t max_live = split ? std::max<int64_t>(4 * n, 1024) : 0;
-  const int64_t wsb = needs_serial(scene, rays) ? optb_workspace_bytes(scene, n, 64 * std::max<int64_t>(n, 16))
+  const int64_t wsb = needs_serial(scene, rays, prm) ? optb_workspace_bytes(scene, n, 64 * std::max<int64_t>(n, 16))
                                                : (int64_t)ws_layout(n, max_live, split).total;
   const int nfam = std::max(prm->n_families, 1);
   size_t need = 256 * 64 + (size_t)n * (8 * 13 + 8) + (size_t)segcap * (13 * 8 + 16) + (size_t)hitcap * (10 * 8 + 12) +

@@ -116,3 +116,16 @@ def test_full_size_properties_c2(engine):
     # a 4f relay images the input plane inverted: monitor-1 position = -input position within aberrations
     r1 = dt.t["hit_root"][:nh][mon == 1].long()
     assert float((py[mon == 1] + oy[r1]).abs().max()) < 0.05 and float((pz[mon == 1] + oz[r1]).abs().max()) < 0.05
+
+
+def test_c5_ripa_7689_leaves(engine):
+    """The full ripa_gen2_lensless scene (scene tables 2.8 MB: read through L2, not staged in shared memory):
+    2,000 jittered rays x 48 pops against the oracle; caps of 1e5 cannot bind -> parallel path."""
+    import optable_b200 as ob
+
+    sc = scenes.ripa(ob, n_rays=0)
+    p = sc.params
+    arrs = scenes.ray_arrays(2000, p["origin"], [0, p["R1w0"], p["R1w0"]], p["direction"], [0, 1e-3, 1e-3],
+                             wavelengths=(p["wavelength"],), w0=p["R1w0"])
+    got, _ = _both(engine, sc, arrs, limit=48, max_live=200_000)
+    assert int(got["counters"][1]) > 40 * 2000
