@@ -32,19 +32,77 @@ BYTES_PER_INTERACTION = 208  # read + write one 104-B ray record pe
 FLOPS_PER_INTERACTION = 1832  # executed (2*DFMA + DMUL + DADD) / interactions, profiles/r1_trace_kernel_summary.md
 
 
-def build_scene():
+def _workloads():
+    """name -> (scene builder, bundle maker(n, start), params). c2 is the benchmark of record (BASELINE configs[1]);
+    the others size up the remaining configs of SURVEY 8(d) for information (`--workload`)."""
+    import numpy as np
+
     import optable_b200 as ob
-    from optable_b200.flatten import FlatScene
+    from optable_b200.bundle import RayBundle, uniform01
     from tests import scenes
 
-    sc = scenes.telescope_4f(ob, n_rays=0)
+    def c2_scene():
+        return scenes.telescope_4f(ob, n_rays=0)
+
+    def c2_rays(n, start):
+        return RayBundle.collimated_disc(n, start=start, x0=-10.0, radius=3.0, wavelength=780e-7, w0=61e-4)
+
+    def c3_scene():
+        mk = lambda x: ob.Doublet([x, 0, 0], CT1=1.359, CT2=0.6, R1=18.405, R2=-13.734, R3=-39.933,
+                                  n12=ob.Glass_NBK7(), n23=ob.Glass_NSF5(), diameter=7.5)
+        return scenes.Scene([mk(30.3964), mk(90.3964)], [], [ob.Monitor([150, 0, 0], 10, 10)])
+
+    def c3_rays(n, start):
+        b = RayBundle.collimated_disc(n, start=start, x0=0.0, radius=3.0, wavelength=780e-7, w0=61e-4)
+        wl = np.linspace(400e-7, 1100e-7, 16)[(np.arange(start, start + n) % 16)]
+        b.columns["wavelength"] = wl
+        b.columns["q_im"] = np.pi * 61e-4 ** 2 / wl
+        return b
+
+    def c4_scene():
+        return scenes.cavity(ob, 0.0, 0.0)
+
+    def c4_rays(n, start):
+        idx = np.arange(start, start + n, dtype=np.uint64)
+        u = [uniform01(idx, k) for k in range(4)]
+        d = np.stack([np.ones(n), (2 * u[2] - 1) * 2e-5, (2 * u[3] - 1) * 2e-5], 1)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        b = RayBundle.collimated_disc(n, start=start, x0=2.0, wavelength=780e-7, w0=61e-4)
+        b.columns.update(oy=2 * u[0] - 1, oz=2 * u[1] - 1, dx=d[:, 0].copy(), dy=d[:, 1].copy(), dz=d[:, 2].copy())
+        return b
+
+    def c5_scene():
+        return scenes.ripa(ob, n_rays=0)
+
+    def c5_rays(n, start):
+        p = scenes.ripa(ob, n_rays=0).params
+        idx = np.arange(start, start + n, dtype=np.uint64)
+        u = [uniform01(idx, k) for k in range(4)]
+        o, d0, w0 = p["origin"], p["direction"], p["R1w0"]
+        d = np.stack([np.full(n, d0[0]), d0[1] + (2 * u[2] - 1) * 1e-3, d0[2] + (2 * u[3] - 1) * 1e-3], 1)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        b = RayBundle.collimated_disc(n, start=start, x0=o[0], wavelength=p["wavelength"], w0=w0)
+        b.columns.update(oy=o[1] + (2 * u[0] - 1) * w0, oz=o[2] + (2 * u[1] - 1) * w0,
+                         dx=d[:, 0].copy(), dy=d[:, 1].copy(), dz=d[:, 2].copy())
+        return b
+
+    return {
+        "c2_4f_telescope": (c2_scene, c2_rays, dict(max_trace_num=2000, rays=10_000_000, rows_per_ray=2)),
+        "c3_doublets_16wl": (c3_scene, c3_rays, dict(max_trace_num=2000, rays=10_000_000, rows_per_ray=1)),
+        "c4_cavity_4000": (c4_scene, c4_rays, dict(max_trace_num=4001, rays=1_000_000, rows_per_ray=0)),
+        "c5_ripa_64": (c5_scene, c5_rays, dict(max_trace_num=64, rays=1_000_000, rows_per_ray=64)),
+    }
+
+
+def build_scene(workload=WORKLOAD):
+    from optable_b200.flatten import FlatScene
+
+    sc = _workloads()[workload][0]()
     return FlatScene(sc.components, sc.monitors)
 
 
-def make_bundle(n, start):
-    from optable_b200.bundle import RayBundle
-
-    return RayBundle.collimated_disc(n, start=start, x0=-10.0, radius=3.0, wavelength=780e-7, w0=61e-4)
+def make_bundle(n, start, workload=WORKLOAD):
+    return _workloads()[workload][1](n, start)
 
 
 class ClockSampler(threading.Thread):
@@ -78,16 +136,17 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_arm(flat, n_sample, threads, repeats=1):
+def cpu_arm(flat, n_sample, threads, repeats=1, workload=WORKLOAD):
     """Oracle port of the reference on the host cores: interactions/s on the first n_sample rays of the workload."""
     from oracle import oracle as O
 
-    arrs = make_bundle(n_sample, 0).materialise()
+    arrs = make_bundle(n_sample, 0, workload).materialise()
+    max_trace = _workloads()[workload][2]["max_trace_num"]
     best = None
     inter = 0
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out = O.trace(flat, arrs, record_segments=False, record_hits=False, nthreads=threads)
+        out = O.trace(flat, arrs, max_trace_num=max_trace, record_segments=False, record_hits=False, nthreads=threads)
         dt = time.perf_counter() - t0
         inter = int(out["counters"][1])
         best = dt if best is None else min(best, dt)
@@ -98,23 +157,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    flat = build_scene()
+    flat = build_scene(args.workload)
     threads = os.cpu_count() or 1
     n_sample = args.ref_rays
     for _ in range(args.warmup):
-        cpu_arm(flat, max(n_sample // 10, 1000), threads)
+        cpu_arm(flat, max(n_sample // 10, 100), threads, workload=args.workload)
     t0 = time.perf_counter()
     total = 0
     for _ in range(args.steps):
-        _, inter, _ = cpu_arm(flat, n_sample, threads)
+        _, inter, _ = cpu_arm(flat, n_sample, threads, workload=args.workload)
         total += inter
     dt = time.perf_counter() - t0
     value = total / dt
-    sample = f"first {n_sample} rays of the {WORKLOAD} batch per step, oracle/optb_oracle.c (C port of the reference), {threads} threads"
+    sample = f"first {n_sample} rays of the {args.workload} batch per step, oracle/optb_oracle.c (C port of the reference), {threads} threads"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step": n_sample, "surfaces": int(flat.n_leaves), "monitors": int(flat.n_monitors)},
+            "config": {"workload": args.workload, "rays_per_step": n_sample, "surfaces": int(flat.n_leaves), "monitors": int(flat.n_monitors)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -137,12 +196,13 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = f"cuda:{local}"
     engine = Engine.get(local)
-    flat = build_scene()
-    n = args.rays
-    bundle = make_bundle(n, start=rank * n)  # weak scaling: every rank traces its own n rays of the endless bundle
+    flat = build_scene(args.workload)
+    wprm = _workloads()[args.workload][2]
+    n = args.rays or wprm["rays"]
+    bundle = make_bundle(n, rank * n, args.workload)  # weak scaling: every rank traces its own n rays of the endless bundle
     rays_dev = bundle.to_torch(device=dev)
-    hit_cap = n * flat.n_monitors
-    dt = DeviceTrace(engine, flat, n, hit_cap, record_hist=True)
+    hit_cap = n * wprm["rows_per_ray"] + 1024
+    dt = DeviceTrace(engine, flat, n, hit_cap, record_hist=True, max_trace_num=wprm["max_trace_num"])
     stream = torch.cuda.current_stream()
 
     def merge_monitors():
@@ -228,7 +288,7 @@ def run_cuda(args):
         te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
-    assert int(hc[A.C_INTERACTIONS]) == inter_per_step
+    assert int(hc[A.C_STATUS]) == 0 and int(hc[A.C_INTERACTIONS]) == inter_per_step, (hc.tolist(), inter_per_step)
     e2e_value = inter_all * e2e_steps / e2e_s
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = hits_per_step * dt.hit_row_bytes() + hy.numel() * 8 + hyz.numel() * 8 + A.C_COUNT * 8
@@ -249,15 +309,15 @@ def run_cuda(args):
                 "note": "kernel is FP64-pipe bound, not HBM bound: see roofline_fp64 and DESIGN.md"}
     fp64_peak = engine.fp64_peak_tflops()
     roofline_fp64 = {"bound": "fp64", "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured in-run (DFMA chain kernel)"}
-    if FLOPS_PER_INTERACTION:
+    if FLOPS_PER_INTERACTION and args.workload == WORKLOAD:
         af = FLOPS_PER_INTERACTION * inter_per_step / (trace_ms * 1e-3) / 1e12
         roofline_fp64.update({"achieved": af, "frac": af / fp64_peak})
     threads = os.cpu_count() or 1
-    cpu_val, cpu_inter, cpu_dt = cpu_arm(flat, args.cpu_rays, threads)
+    cpu_val, cpu_inter, cpu_dt = cpu_arm(flat, args.cpu_rays, threads, workload=args.workload)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu": n, "surfaces": int(flat.n_leaves), "monitors": int(flat.n_monitors),
+            "config": {"workload": args.workload, "rays_per_gpu": n, "surfaces": int(flat.n_leaves), "monitors": int(flat.n_monitors),
                        "interactions_per_step_per_gpu": inter_per_step, "monitor_rows_per_step_per_gpu": hits_per_step,
                        "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2" % ((h2d + d2h) / 1e9),
                        "parallelism": f"rays sharded over {world} GPU(s), scene tables replicated"},
@@ -279,7 +339,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--rays", type=int, default=10_000_000, help="rays per GPU per step")
+    ap.add_argument("--rays", type=int, default=0, help="rays per GPU per step (0 = the workload's default)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["c2_4f_telescope", "c3_doublets_16wl", "c4_cavity_4000", "c5_ripa_64"])
     ap.add_argument("--cpu-rays", type=int, default=400_000, help="bounded sample for the in-run CPU baseline")
     ap.add_argument("--ref-rays", type=int, default=400_000, help="rays per step of the reference arm")
     ap.add_argument("--e2e-steps", type=int, default=5)

@@ -126,8 +126,10 @@ class DeviceTrace:
                                       n_rays, slack)
         self.hit_columns = tuple(k for k in HIT_COLUMNS_ALL if k in self.t)
 
-    def run(self, rays_t):
-        self.engine.trace_device(self.scene, rays_t, self.prm, self.res)
+    def run(self, rays_t, max_live=None):
+        if self.flat.n_capslots:
+            self.t["cap_counts"].zero_()  # a bundle is a fresh set of ray ids every time
+        self.engine.trace_device(self.scene, rays_t, self.prm, self.res, max_live)
 
     def counters(self):
         return self.t["counters"].cpu().numpy()

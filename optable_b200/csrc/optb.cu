@@ -913,15 +913,29 @@ struct ArenaCursor {
 };
 }  // namespace
 
+static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
+                           optb_result* out, int64_t live_factor);
+
 extern "C" int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
                                optb_result* out) {
   if (!ctx || !scene || !rays || !prm || !out) return -1;
+  // The live ray set of a splitting scene is not known in advance: grow the workspace until it fits.
+  for (int64_t factor = 4; factor <= 1024; factor *= 4) {
+    int rc = trace_host_once(ctx, scene, rays, prm, out, factor);
+    if (rc) return rc;
+    if (!(ctx->h_counters[OPTB_C_STATUS] & OPTB_ST_WORK_OVERFLOW)) return 0;
+  }
+  return fail(ctx, -8, "live ray set exceeds 1024x the batch: workspace overflow");
+}
+
+static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
+                           optb_result* out, int64_t live_factor) {
   cudaSetDevice(ctx->device);
   const int64_t n = rays->n;
   const bool split = needs_wavefront(scene, prm) || needs_serial(scene, rays, prm);
   const int64_t segcap = prm->record_segments ? out->seg_capacity : 0, hitcap = prm->record_hits ? out->hit_capacity : 0;
-  const int64_t max_live = split ? std::max<int64_t>(4 * n, 1024) : 0;
-  const int64_t wsb = needs_serial(scene, rays, prm) ? optb_workspace_bytes(scene, n, 64 * std::max<int64_t>(n, 16))
+  const int64_t max_live = split ? std::max<int64_t>(live_factor * n, 1024) : 0;
+  const int64_t wsb = needs_serial(scene, rays, prm) ? optb_workspace_bytes(scene, n, 16 * live_factor * std::max<int64_t>(n, 16))
                                                : (int64_t)ws_layout(n, max_live, split).total;
   const int nfam = std::max(prm->n_families, 1);
   size_t need = 256 * 64 + (size_t)n * (8 * 13 + 8) + (size_t)segcap * (13 * 8 + 16) + (size_t)hitcap * (10 * 8 + 12) +
@@ -973,6 +987,7 @@ extern "C" int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const opt
   void* ws = ac.take((size_t)wsb);
   if (!ws || !dv.counters) return fail(ctx, -9, "arena sizing");
   if (scene->n_caps > 0 && out->cap_counts) CK(cudaMemcpyAsync(dv.cap_counts, out->cap_counts, capb, cudaMemcpyHostToDevice, st), "H2D caps");
+  else CK(cudaMemsetAsync(dv.cap_counts, 0, capb, st), "memset caps");  // no table given: every family starts at zero
   int rc = optb_trace(ctx, scene, &dr, prm, &dv, ws, wsb, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->h_counters, dv.counters, OPTB_C_COUNT * 8, cudaMemcpyDeviceToHost, st), "D2H counters");

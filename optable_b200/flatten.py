@@ -118,7 +118,9 @@ class FlatScene:
         self.capslots = []     # cap slot -> component object
         self.max_children = 0  # most rays one interaction can emit (<=1: no splitting anywhere)
         for c in components:
-            self._visit(c, in_group=False)
+            tree = self._visit(c, in_group=False)
+            if tree is not None:
+                self._emit(tree)
         self.node_i = np.ascontiguousarray(np.array(self._ni, dtype=np.int32).reshape(-1, A.NI_STRIDE))
         self.node_f = np.ascontiguousarray(np.array(self._nf, dtype=np.float64).reshape(-1, A.NF_STRIDE))
         self.mat_kind = np.array(self._mats.kind or [0], dtype=np.int32)
@@ -141,36 +143,70 @@ class FlatScene:
         self.n_capslots = len(self.capslots)
 
     # -- tree walk ---------------------------------------------------------------------------
-    def _new_node(self):
-        self._ni.append([0] * A.NI_STRIDE)
-        self._nf.append([0.0] * A.NF_STRIDE)
-        ni = self._ni[-1]
+    # Large groups get synthetic sub-groups over contiguous runs of children (a BVH in list order). The box of a
+    # synthetic group is the union of its members' own boxes, and the slab test is monotone under box inclusion
+    # (bit for bit: subtraction and multiplication by a fixed reciprocal are monotone in floating point), so a
+    # child whose box the ray hits is never culled by a wrapper: the set of leaves that get tested, and their
+    # order, are exactly the reference's (component_group.py:104-115), only reached in O(log n) box tests.
+    BVH_FANOUT = 8
+    BVH_MIN_CHILDREN = 24
+
+    @staticmethod
+    def _blank():
+        ni, nf = [0] * A.NI_STRIDE, [0.0] * A.NF_STRIDE
         ni[A.NI_CAPSLOT] = -1
         ni[A.NI_LEAF] = -1
-        return len(self._ni) - 1
+        return ni, nf
+
+    def _emit(self, tree):
+        """Append a (sub)tree in pre-order; `skip` = index of the first node after the subtree."""
+        ni, nf, children = tree
+        self._ni.append(ni)
+        self._nf.append(nf)
+        for child in children:
+            self._emit(child)
+        ni[A.NI_SKIP] = len(self._ni)
+
+    def _wrap_runs(self, children):
+        """Group consecutive children F at a time under synthetic box nodes until at most F entries remain."""
+        F = self.BVH_FANOUT
+        level = children
+        while len(level) > F:
+            nxt = []
+            for k in range(0, len(level), F):
+                run = level[k:k + F]
+                if len(run) == 1:
+                    nxt.append(run[0])
+                    continue
+                ni, nf = self._blank()
+                ni[A.NI_GEOM], ni[A.NI_AABB] = A.G_GROUP, 1
+                boxes = np.array([c[1][A.NF_AABB:A.NF_AABB + 6] for c in run], dtype=np.float64)
+                lo, hi = boxes[:, 0::2].min(axis=0), boxes[:, 1::2].max(axis=0)
+                nf[A.NF_AABB:A.NF_AABB + 6] = [float(lo[0]), float(hi[0]), float(lo[1]), float(hi[1]), float(lo[2]), float(hi[2])]
+                nxt.append((ni, nf, run))
+            level = nxt
+        return level
 
     def _visit(self, comp, in_group):
+        """Component (sub)tree -> (node_i row, node_f row, children) or None when nothing can be hit."""
         if hasattr(comp, "components") and "ComponentGroup" in _mro_names(comp):
             if len(comp.components) == 0:
-                return  # nothing to hit (the reference would raise in merge_bboxs on first use)
-            idx = self._new_node()
-            ni, nf = self._ni[idx], self._nf[idx]
+                return None  # nothing to hit (the reference would raise in merge_bboxs on first use)
+            ni, nf = self._blank()
             ni[A.NI_GEOM] = A.G_GROUP
             ni[A.NI_AABB] = 1
             nf[A.NF_AABB:A.NF_AABB + 6] = [float(v) for v in comp.bbox]
-            for child in comp.components:
-                self._visit(child, in_group=True)
-            ni[A.NI_SKIP] = len(self._ni)
-            return
+            children = [t for t in (self._visit(child, in_group=True) for child in comp.components) if t is not None]
+            if len(children) >= self.BVH_MIN_CHILDREN:
+                children = self._wrap_runs(children)
+            return ni, nf, children
         names = _mro_names(comp)
         sname = type(comp.surface).__name__
         if "PointObj" in names or sname == "Point":
-            return  # Point.f = |P| never changes sign -> never hit (surfaces.py:68-86)
+            return None  # Point.f = |P| never changes sign -> never hit (surfaces.py:68-86)
         if "Monitor" in names:
             raise FlattenError("a Monitor inside table.components is a pass-through that re-hits itself; unsupported")
-        idx = self._new_node()
-        ni, nf = self._ni[idx], self._nf[idx]
-        ni[A.NI_SKIP] = idx + 1
+        ni, nf = self._blank()
         ni[A.NI_AABB] = 1 if in_group else 0
         ni[A.NI_LEAF] = len(self.leaves)
         self.leaves.append(comp)
@@ -187,6 +223,7 @@ class FlatScene:
             ni[A.NI_CAPSLOT] = len(self.capslots)
             nf[A.NF_CAPMAX] = float(cap)
             self.capslots.append(comp)
+        return ni, nf, []
 
     def _poly_record(self, s):
         off = len(self._aux)
