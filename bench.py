@@ -202,7 +202,7 @@ def run_cuda(args):
     bundle = make_bundle(n, rank * n, args.workload)  # weak scaling: every rank traces its own n rays of the endless bundle
     rays_dev = bundle.to_torch(device=dev)
     hit_cap = n * wprm["rows_per_ray"] + 1024
-    dt = DeviceTrace(engine, flat, n, hit_cap, record_hist=True, max_trace_num=wprm["max_trace_num"])
+    dt = DeviceTrace(engine, flat, n, hit_cap, record_hist=True, max_trace_num=wprm["max_trace_num"], chain_len=args.chain_len)
     stream = torch.cuda.current_stream()
 
     def merge_monitors():
@@ -344,6 +344,7 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=400_000, help="bounded sample for the in-run CPU baseline")
     ap.add_argument("--ref-rays", type=int, default=400_000, help="rays per step of the reference arm")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--chain-len", type=int, default=0, help="max in-register pops per launch (0 = unlimited); scheduling only")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3

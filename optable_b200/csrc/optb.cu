@@ -43,7 +43,7 @@ struct Header {  // first bytes of the workspace
   unsigned int pad[14];
 };
 
-struct SceneOff { uint32_t nf, ni, matk, matf, mon, aux; };
+struct SceneOff { uint32_t trav, nf, ni, matk, matf, mon, aux; };
 
 struct TraceArgs {
   const unsigned char* blob; uint32_t blob_bytes; SceneOff off; int n_nodes, n_mons;
@@ -258,9 +258,10 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   while (true) {
     int leaf = -1;
     while (i < n) {
-      const int32_t* ni = sv.ni + i * OPTB_NI_STRIDE;
-      if (ni[OPTB_NI_AABB] && !slab_hit(br, sv.nf + i * OPTB_NF_STRIDE + OPTB_NF_AABB)) { i = ni[OPTB_NI_SKIP]; continue; }
-      const int g = ni[OPTB_NI_GEOM];
+      const double* tv = sv.trav + i * 8;
+      const int2 gs = *reinterpret_cast<const int2*>(tv + 6);  // {geometry kind, skip}
+      if (*reinterpret_cast<const int*>(tv + 7) && !slab_hit(br, tv)) { i = gs.y; continue; }
+      const int g = gs.x;
       const int cur = i++;
       if (g == OPTB_G_GROUP) continue;
       if (g == OPTB_G_ASPHERE && n_parked < kPark) {
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
     base = smem_raw;
   }
   SceneView sv;
+  sv.trav = (const double*)(base + a.off.trav);
   sv.nf = (const double*)(base + a.off.nf);
   sv.ni = (const int32_t*)(base + a.off.ni);
   sv.matk = (const int32_t*)(base + a.off.matk);
@@ -500,43 +502,39 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restric
   }
 }
 
+// Thread t of a block handles parents base + sub*256 + t for sub = 0..7: reads of the sparse child slots and
+// writes of the packed wavefront are both (nearly) coalesced; a running carry keeps the global order.
 __global__ void __launch_bounds__(kScanBlock) scatter_kernel(const uint8_t* __restrict__ nchild, long long n,
                                                              const unsigned int* __restrict__ tile_base, RayBuf c, RayBuf w,
                                                              const Header* hdr) {
   __shared__ unsigned int s_warp[kScanBlock / 32];
+  __shared__ unsigned int s_carry;
   if (hdr->n_next == 0) return;
-  constexpr int kPer = kTile / kScanBlock;  // consecutive entries per thread
-  long long i0 = (long long)blockIdx.x * kTile + (long long)threadIdx.x * kPer;
-  unsigned int cnt[kPer];
-  unsigned int mine = 0;
-#pragma unroll
-  for (int k = 0; k < kPer; k++) {
-    long long i = i0 + k;
-    cnt[k] = (i < n) ? nchild[i] : 0u;
-    mine += cnt[k];
-  }
-  // block exclusive scan of `mine`
-  unsigned int incl = mine;
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[wid] = incl;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = tile_base[blockIdx.x];
   __syncthreads();
-  unsigned int woff = 0;
-  for (int k = 0; k < wid; k++) woff += s_warp[k];
-  unsigned int off = tile_base[blockIdx.x] + woff + incl - mine;
-#pragma unroll
-  for (int k = 0; k < kPer; k++) {
-    long long i = i0 + k;
-    for (unsigned int j = 0; j < cnt[k]; j++) {
-      long long src = 2 * i + j;
-      long long dst = off++;
+  for (int sub = 0; sub < kTile / kScanBlock; sub++) {
+    const long long i = (long long)blockIdx.x * kTile + (long long)sub * kScanBlock + threadIdx.x;
+    const unsigned int mine = (i < n) ? nchild[i] : 0u;
+    unsigned int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    unsigned int woff = 0, total = 0;
+    for (int k = 0; k < kScanBlock / 32; k++) { if (k < wid) woff += s_warp[k]; total += s_warp[k]; }
+    const unsigned int off = s_carry + woff + incl - mine;
+    for (unsigned int j = 0; j < mine; j++) {
+      const long long src = 2 * i + j, dst = (long long)off + j;
 #pragma unroll
       for (int f = 0; f < kRayF64; f++) w.f[f][dst] = c.f[f][src];
       w.flags[dst] = c.flags[src]; w.root[dst] = c.root[src]; w.pop[dst] = c.pop[src]; w.family[dst] = c.family[src];
     }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
   }
 }
 
@@ -659,6 +657,8 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   size_t b_mk = (size_t)d->n_materials * 4, b_mf = (size_t)d->n_materials * OPTB_MF_STRIDE * 8;
   size_t b_mon = (size_t)std::max(d->n_monitors, 1) * OPTB_MON_STRIDE * 8, b_aux = (size_t)std::max<long long>(d->n_aux, 1) * 8;
   size_t o = 0;
+  const size_t b_trav = (size_t)std::max(d->n_nodes, 1) * 64;
+  s->off.trav = (uint32_t)o; o = align_up(o + b_trav, 16);
   s->off.nf = (uint32_t)o; o = align_up(o + b_nf, 16);
   s->off.ni = (uint32_t)o; o = align_up(o + b_ni, 16);
   s->off.matk = (uint32_t)o; o = align_up(o + b_mk, 16);
@@ -671,6 +671,13 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   if (d->n_nodes) {
     memcpy(host.data() + s->off.nf, d->node_f, b_nf);
     memcpy(host.data() + s->off.ni, d->node_i, b_ni);
+    for (int i = 0; i < d->n_nodes; i++) {  // compact traversal records
+      unsigned char* tv = host.data() + s->off.trav + (size_t)i * 64;
+      const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
+      memcpy(tv, d->node_f + (size_t)i * OPTB_NF_STRIDE + OPTB_NF_AABB, 48);
+      const int32_t pack[4] = {ni[OPTB_NI_GEOM], ni[OPTB_NI_SKIP], ni[OPTB_NI_AABB], 0};
+      memcpy(tv + 48, pack, 16);
+    }
   }
   memcpy(host.data() + s->off.matk, d->mat_kind, b_mk);
   memcpy(host.data() + s->off.matf, d->mat_f, b_mf);

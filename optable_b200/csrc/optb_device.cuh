@@ -30,6 +30,8 @@ struct Ray {
 
 // Pointers into the staged scene tables (shared memory when they fit, else global/L2).
 struct SceneView {
+  const double* trav;  // 64 B per node: lab AABB (6 doubles) + {geometry kind, skip} + {box-test flag, pad}: all the
+                       // pre-order walk reads; the 368-B node rows are only touched for leaves that get tested
   const double* nf;
   const int32_t* ni;
   const int32_t* matk;
