@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -148,8 +149,8 @@ class FlatScene:
     # (bit for bit: subtraction and multiplication by a fixed reciprocal are monotone in floating point), so a
     # child whose box the ray hits is never culled by a wrapper: the set of leaves that get tested, and their
     # order, are exactly the reference's (component_group.py:104-115), only reached in O(log n) box tests.
-    BVH_FANOUT = 8
-    BVH_MIN_CHILDREN = 24
+    BVH_FANOUT = int(os.environ.get("OPTB_BVH_FANOUT", "4"))
+    BVH_MIN_CHILDREN = int(os.environ.get("OPTB_BVH_MIN_CHILDREN", "9"))
 
     @staticmethod
     def _blank():
@@ -167,25 +168,55 @@ class FlatScene:
             self._emit(child)
         ni[A.NI_SKIP] = len(self._ni)
 
+    def _synthetic(self, members):
+        """A box-only group node over `members` (list of trees); box = union of the members' own boxes."""
+        ni, nf = self._blank()
+        ni[A.NI_GEOM], ni[A.NI_AABB] = A.G_GROUP, 1
+        boxes = np.array([m[1][A.NF_AABB:A.NF_AABB + 6] for m in members], dtype=np.float64)
+        lo, hi = boxes[:, 0::2].min(axis=0), boxes[:, 1::2].max(axis=0)
+        nf[A.NF_AABB:A.NF_AABB + 6] = [float(lo[0]), float(hi[0]), float(lo[1]), float(hi[1]), float(lo[2]), float(hi[2])]
+        return ni, nf, members
+
     def _wrap_runs(self, children):
-        """Group consecutive children F at a time under synthetic box nodes until at most F entries remain."""
-        F = self.BVH_FANOUT
-        level = children
-        while len(level) > F:
-            nxt = []
-            for k in range(0, len(level), F):
-                run = level[k:k + F]
-                if len(run) == 1:
-                    nxt.append(run[0])
-                    continue
-                ni, nf = self._blank()
-                ni[A.NI_GEOM], ni[A.NI_AABB] = A.G_GROUP, 1
-                boxes = np.array([c[1][A.NF_AABB:A.NF_AABB + 6] for c in run], dtype=np.float64)
-                lo, hi = boxes[:, 0::2].min(axis=0), boxes[:, 1::2].max(axis=0)
-                nf[A.NF_AABB:A.NF_AABB + 6] = [float(lo[0]), float(hi[0]), float(lo[1]), float(hi[1]), float(lo[2]), float(hi[2])]
-                nxt.append((ni, nf, run))
-            level = nxt
-        return level
+        """Hierarchy over a child list that keeps the list order: every node covers a contiguous run, runs are cut
+        where the surface-area heuristic is cheapest (for a row-major array: first between rows, then inside a
+        row), at most BVH_FANOUT runs per node."""
+        boxes = np.array([c[1][A.NF_AABB:A.NF_AABB + 6] for c in children], dtype=np.float64)
+        F = max(2, self.BVH_FANOUT)
+
+        def area(lo, hi):
+            d = np.maximum(hi - lo, 0.0)
+            return 2.0 * (d[..., 0] * d[..., 1] + d[..., 1] * d[..., 2] + d[..., 2] * d[..., 0]) + 1e-300
+
+        def best_cut(a, b):
+            """Cheapest cut of [a, b) into [a, s) + [s, b); returns (cost, s)."""
+            blo, bhi = boxes[a:b, 0::2], boxes[a:b, 1::2]
+            pl, ph = np.minimum.accumulate(blo, 0), np.maximum.accumulate(bhi, 0)
+            sl, sh = np.minimum.accumulate(blo[::-1], 0)[::-1], np.maximum.accumulate(bhi[::-1], 0)[::-1]
+            k = np.arange(1, b - a)
+            cost = area(pl[:-1], ph[:-1]) * k + area(sl[1:], sh[1:]) * (b - a - k)
+            j = int(np.argmin(cost))
+            return float(cost[j]), a + 1 + j
+
+        def build(a, b):
+            """Trees that stand for the run [a, b) inside its parent (at most F of them)."""
+            if b - a <= F:
+                return list(children[a:b])
+            parts = [(a, b)]
+            while len(parts) < F:
+                # cut the part whose cut saves the most (largest part first is a good proxy and O(n log n))
+                k = max(range(len(parts)), key=lambda i: parts[i][1] - parts[i][0])
+                pa, pb = parts[k]
+                if pb - pa < 2:
+                    break
+                _, s = best_cut(pa, pb)
+                parts[k:k + 1] = [(pa, s), (s, pb)]
+            out = []
+            for pa, pb in parts:
+                out.append(children[pa] if pb - pa == 1 else self._synthetic(build(pa, pb)))
+            return out
+
+        return build(0, len(children))
 
     def _visit(self, comp, in_group):
         """Component (sub)tree -> (node_i row, node_f row, children) or None when nothing can be hit."""
