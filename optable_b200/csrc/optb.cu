@@ -11,6 +11,7 @@
 //   mark_kernel       first/last wavefront index of every root (rank of a ray inside its root's generation).
 // Segments and monitor rows are appended with warp-aggregated atomics and carry their (root, pop) key.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
@@ -62,6 +63,7 @@ struct TraceArgs {
   // family-serial mode (scenes with interact caps): one thread owns one Ray._id family and replays the
   // reference's sequential order; w is then a per-family FIFO ring of qcap entries
   const uint32_t* fam_off; uint32_t* fam_roots; uint32_t qcap;
+  uint32_t root_base;  // global index of ray 0 of this launch (chunked host traces)
 };
 
 OPTB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,8 +110,8 @@ OPTB_DEV void load_ray(const TraceArgs& a, long long i, Ray& r, bool& solo, uint
     r.len = s.length ? OPTB_COL(s.length, 12) : INFINITY;
 #undef OPTB_COL
     r.flags = s.flags ? s.flags[i] : (OPTB_RF_ALIVE | OPTB_RF_HASQ);
-    r.root = (uint32_t)i; r.pop = 0;
-    r.family = s.family ? s.family[i] : (int32_t)i;
+    r.root = (uint32_t)i + a.root_base; r.pop = 0;
+    r.family = s.family ? s.family[i] : (int32_t)r.root;
     solo = true; gcount = 1;
   } else {
     const RayBuf& w = a.w;
@@ -591,6 +593,8 @@ struct optb_ctx {
   void* arena; size_t arena_bytes;
   unsigned long long* h_counters;  // pinned
   unsigned int* h_hdr;             // pinned
+  cudaStream_t s_h2d, s_run, s_d2h;  // pipelined optb_trace_host
+  unsigned long long* h_chunk; size_t h_chunk_n;  // pinned per-chunk counters
 };
 
 struct optb_scene {
@@ -637,6 +641,8 @@ extern "C" int optb_ctx_destroy(optb_ctx* ctx) {
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
+  if (ctx->h_chunk) cudaFreeHost(ctx->h_chunk);
+  if (ctx->s_h2d) { cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_run); cudaStreamDestroy(ctx->s_d2h); }
   delete ctx;
   return 0;
 }
@@ -782,10 +788,19 @@ extern "C" int64_t optb_workspace_bytes(const optb_scene* scene, int64_t n_rays,
   return need;
 }
 
+static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
+                      optb_result* out, void* workspace, int64_t workspace_bytes, cudaStream_t st, uint32_t root_base,
+                      bool zero_hist);
+
 extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
                           optb_result* out, void* workspace, int64_t workspace_bytes, void* stream_v) {
   if (!ctx || !scene || !rays || !prm || !out) return -1;
-  cudaStream_t st = (cudaStream_t)stream_v;
+  return trace_impl(ctx, scene, rays, prm, out, workspace, workspace_bytes, (cudaStream_t)stream_v, 0u, true);
+}
+
+static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
+                      optb_result* out, void* workspace, int64_t workspace_bytes, cudaStream_t st, uint32_t root_base,
+                      bool zero_hist) {
   cudaSetDevice(ctx->device);
   if (!out->counters) return fail(ctx, -7, "result.counters is required");
   if (rays->n >= 0xffffffffll) return fail(ctx, -7, "at most 2^32-1 rays per call");
@@ -830,7 +845,8 @@ extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_ray
 
   CK(cudaMemsetAsync(out->counters, 0, sizeof(int64_t) * OPTB_C_COUNT, st), "memset counters");
   CK(cudaMemsetAsync(hdr, 0, sizeof(Header), st), "memset header");
-  if (prm->record_hist && scene->n_mons) {
+  if (prm->record_hist && scene->n_mons && !out->hist_y) return fail(ctx, -7, "record_hist needs hist_y and hist_yz");
+  if (prm->record_hist && scene->n_mons && zero_hist) {
     if (!out->hist_y || !out->hist_yz) return fail(ctx, -7, "record_hist needs hist_y and hist_yz");
     CK(cudaMemsetAsync(out->hist_y, 0, sizeof(int64_t) * OPTB_HIST_BINS * scene->n_mons, st), "memset hist");
     CK(cudaMemsetAsync(out->hist_yz, 0, sizeof(int64_t) * OPTB_HIST_BINS * OPTB_HIST_BINS * scene->n_mons, st), "memset hist");
@@ -849,6 +865,7 @@ extern "C" int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_ray
   a.out = *out;
   a.counters = (unsigned long long*)out->counters;
   a.hdr = hdr;
+  a.root_base = root_base;
   if (split) {
     a.w = make_raybuf(ws + L.w, cap);
     a.c = make_raybuf(ws + L.c, 2 * cap);
@@ -923,9 +940,167 @@ struct ArenaCursor {
 static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
                            optb_result* out, int64_t live_factor);
 
+// Chunked, three-stream version of optb_trace_host for scenes that cannot split: the host->device copy of chunk
+// c+1, the trace of chunk c and the device->host copy of chunk c-1 overlap (PCIe is full duplex). Rows of chunk c
+// land behind the rows of chunks < c, so the host result is the same set of rows as the one-shot path; row keys
+// stay global through root_base. Returns 1 when a chunk overflowed its (estimated) device capacity: the caller
+// then repeats the whole batch on the one-shot path.
+static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
+                                optb_result* out) {
+  cudaSetDevice(ctx->device);
+  constexpr int64_t kChunk = 1 << 20;
+  const int64_t n = rays->n;
+  const int nch = (int)((n + kChunk - 1) / kChunk);
+  const int64_t segcap = prm->record_segments ? out->seg_capacity : 0, hitcap = prm->record_hits ? out->hit_capacity : 0;
+  auto chunk_cap = [&](int64_t total) { return total ? std::min<int64_t>(total, (int64_t)((double)total * kChunk / n * 1.25) + 4096) : 0; };
+  const int64_t cseg = chunk_cap(segcap), chit = chunk_cap(hitcap);
+  const int64_t wsb = (int64_t)ws_layout(kChunk, 0, false).total;
+  if (!ctx->s_h2d) {
+    CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking), "stream");
+    CK(cudaStreamCreateWithFlags(&ctx->s_run, cudaStreamNonBlocking), "stream");
+    CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking), "stream");
+  }
+  if (ctx->h_chunk_n < (size_t)nch) {
+    if (ctx->h_chunk) cudaFreeHost(ctx->h_chunk);
+    ctx->h_chunk = nullptr; ctx->h_chunk_n = 0;
+    CK(cudaMallocHost((void**)&ctx->h_chunk, sizeof(unsigned long long) * OPTB_C_COUNT * nch), "pinned counters");
+    ctx->h_chunk_n = nch;
+  }
+  size_t need = 256 * 128 + (size_t)n * (8 * 13 + 8) + 2 * ((size_t)cseg * (13 * 8 + 16) + (size_t)chit * (10 * 8 + 12)) +
+                (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 8 + 2 * (64 * 8 + (size_t)wsb) + 4096;
+  if (ctx->arena_bytes < need) {
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr; ctx->arena_bytes = 0;
+    CK(cudaMalloc(&ctx->arena, need), "cudaMalloc(arena)");
+    ctx->arena_bytes = need;
+  }
+  ArenaCursor ac{(unsigned char*)ctx->arena, 0, ctx->arena_bytes};
+  // full-length device input columns; chunks are slices of them
+  optb_rays dr = *rays;
+  const double* const* src_f = &rays->ox;
+  const double** dst_f = &dr.ox;
+  for (int f = 0; f < kRayF64; f++) {
+    if (!src_f[f]) { dst_f[f] = nullptr; continue; }
+    const size_t rows = ((rays->broadcast >> f) & 1u) ? 1 : (size_t)n;
+    dst_f[f] = (const double*)ac.take(rows * 8);
+    if (!dst_f[f]) return fail(ctx, -9, "arena sizing");
+    if (rows == 1) CK(cudaMemcpyAsync((void*)dst_f[f], src_f[f], 8, cudaMemcpyHostToDevice, ctx->s_h2d), "H2D rays");
+  }
+  if (rays->flags) dr.flags = (const uint32_t*)ac.take((size_t)n * 4);
+  if (rays->family) dr.family = (const int32_t*)ac.take((size_t)n * 4);
+  struct Col { void* dev[2]; unsigned char* host; size_t elt; int kind; };
+  std::vector<Col> cols;
+  optb_result dv[2] = {*out, *out};
+  auto add = [&](size_t field_off, void* host_ptr, size_t elt, int64_t capn, int kind) {
+    for (int s = 0; s < 2; s++) *(void**)((unsigned char*)&dv[s] + field_off) = nullptr;
+    if (!host_ptr || capn == 0) return;
+    Col c{{ac.take((size_t)capn * elt), ac.take((size_t)capn * elt)}, (unsigned char*)host_ptr, elt, kind};
+    for (int s = 0; s < 2; s++) *(void**)((unsigned char*)&dv[s] + field_off) = c.dev[s];
+    cols.push_back(c);
+  };
+#define OPTB_FIELD(name) offsetof(optb_result, name), (void*)out->name
+  {
+    const size_t seg0 = offsetof(optb_result, seg_ox), hit0 = offsetof(optb_result, hit_px);
+    double* const* seg_h = &out->seg_ox; double* const* hit_h = &out->hit_px;
+    for (int f = 0; f < 13; f++) add(seg0 + 8 * f, seg_h[f], 8, cseg, 0);
+    add(OPTB_FIELD(seg_flags), 4, cseg, 0); add(OPTB_FIELD(seg_root), 4, cseg, 0);
+    add(OPTB_FIELD(seg_pop), 4, cseg, 0); add(OPTB_FIELD(seg_leaf), 4, cseg, 0);
+    add(OPTB_FIELD(hit_monitor), 4, chit, 1); add(OPTB_FIELD(hit_root), 4, chit, 1); add(OPTB_FIELD(hit_pop), 4, chit, 1);
+    for (int f = 0; f < 10; f++) add(hit0 + 8 * f, hit_h[f], 8, chit, 1);
+  }
+#undef OPTB_FIELD
+  for (auto& c : cols) if (!c.dev[0] || !c.dev[1]) return fail(ctx, -9, "arena sizing");
+  const size_t hy = (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * 8, hyz = hy * OPTB_HIST_BINS;
+  int64_t* d_hy = (int64_t*)ac.take(hy); int64_t* d_hyz = (int64_t*)ac.take(hyz);
+  void* ws[2];
+  for (int s = 0; s < 2; s++) {
+    dv[s].seg_capacity = cseg; dv[s].hit_capacity = chit;
+    dv[s].hist_y = d_hy; dv[s].hist_yz = d_hyz; dv[s].cap_counts = nullptr;
+    dv[s].counters = (int64_t*)ac.take(OPTB_C_COUNT * 8);
+    ws[s] = ac.take((size_t)wsb);
+    if (!ws[s] || !dv[s].counters) return fail(ctx, -9, "arena sizing");
+  }
+  if (prm->record_hist && scene->n_mons) {
+    CK(cudaMemsetAsync(d_hy, 0, hy, ctx->s_run), "memset hist");
+    CK(cudaMemsetAsync(d_hyz, 0, hyz, ctx->s_run), "memset hist");
+  }
+  std::vector<cudaEvent_t> ev_h2d(nch), ev_run(nch), ev_d2h(nch);
+  for (int c = 0; c < nch; c++) {
+    cudaEventCreateWithFlags(&ev_h2d[c], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_run[c], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_d2h[c], cudaEventDisableTiming);
+  }
+  unsigned long long tot[OPTB_C_COUNT] = {0};
+  int64_t seg_off = 0, hit_off = 0;
+  bool chunk_overflow = false;
+  int rc = 0;
+  auto drain = [&](int k) -> int {
+    CK(cudaEventSynchronize(ev_run[k]), "sync chunk");
+    const unsigned long long* hc = ctx->h_chunk + (size_t)k * OPTB_C_COUNT;
+    if (hc[OPTB_C_STATUS] & (OPTB_ST_SEG_OVERFLOW | OPTB_ST_HIT_OVERFLOW)) chunk_overflow = true;
+    int64_t rows[2] = {std::min<int64_t>((int64_t)hc[OPTB_C_SEGMENTS], cseg), std::min<int64_t>((int64_t)hc[OPTB_C_HITS], chit)};
+    int64_t room[2] = {segcap - seg_off, hitcap - hit_off};
+    for (int kind = 0; kind < 2; kind++)
+      if (rows[kind] > room[kind]) { rows[kind] = std::max<int64_t>(room[kind], 0); tot[OPTB_C_STATUS] |= kind ? OPTB_ST_HIT_OVERFLOW : OPTB_ST_SEG_OVERFLOW; }
+    for (auto& c : cols) {
+      const int64_t r = rows[c.kind], off = c.kind ? hit_off : seg_off;
+      if (r > 0) CK(cudaMemcpyAsync(c.host + (size_t)off * c.elt, c.dev[k & 1], (size_t)r * c.elt, cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H rows");
+    }
+    CK(cudaEventRecord(ev_d2h[k], ctx->s_d2h), "event");
+    if (prm->record_segments) seg_off += rows[0];
+    if (prm->record_hits) hit_off += rows[1];
+    for (int q : {OPTB_C_SEGMENTS, OPTB_C_INTERACTIONS, OPTB_C_HITS, OPTB_C_TESTS, OPTB_C_DROPPED, OPTB_C_LAUNCHES}) tot[q] += hc[q];
+    tot[OPTB_C_STATUS] |= hc[OPTB_C_STATUS];
+    tot[OPTB_C_GENERATIONS] = std::max(tot[OPTB_C_GENERATIONS], hc[OPTB_C_GENERATIONS]);
+    return 0;
+  };
+  for (int c = 0; c < nch && !rc; c++) {
+    const int64_t lo = (int64_t)c * kChunk, m = std::min<int64_t>(kChunk, n - lo);
+    for (int f = 0; f < kRayF64; f++) {
+      if (!src_f[f] || ((rays->broadcast >> f) & 1u)) continue;
+      CK(cudaMemcpyAsync((void*)(dst_f[f] + lo), src_f[f] + lo, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->s_h2d), "H2D rays");
+    }
+    if (rays->flags) CK(cudaMemcpyAsync((void*)(dr.flags + lo), rays->flags + lo, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->s_h2d), "H2D flags");
+    if (rays->family) CK(cudaMemcpyAsync((void*)(dr.family + lo), rays->family + lo, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->s_h2d), "H2D family");
+    CK(cudaEventRecord(ev_h2d[c], ctx->s_h2d), "event");
+    CK(cudaStreamWaitEvent(ctx->s_run, ev_h2d[c], 0), "wait");
+    if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_run, ev_d2h[c - 2], 0), "wait");  // the result set is free again
+    optb_rays cr = dr;
+    cr.n = m;
+    const double** cf = &cr.ox;
+    for (int f = 0; f < kRayF64; f++) if (cf[f] && !((rays->broadcast >> f) & 1u)) cf[f] += lo;
+    if (cr.flags) cr.flags += lo;
+    if (cr.family) cr.family += lo;
+    rc = trace_impl(ctx, scene, &cr, prm, &dv[c & 1], ws[c & 1], wsb, ctx->s_run, (uint32_t)lo, false);
+    if (rc) break;
+    CK(cudaMemcpyAsync(ctx->h_chunk + (size_t)c * OPTB_C_COUNT, dv[c & 1].counters, OPTB_C_COUNT * 8, cudaMemcpyDeviceToHost, ctx->s_run), "D2H counters");
+    CK(cudaEventRecord(ev_run[c], ctx->s_run), "event");
+    if (c >= 1) rc = drain(c - 1);
+  }
+  if (!rc) rc = drain(nch - 1);
+  if (!rc && prm->record_hist && scene->n_mons) {
+    cudaStreamWaitEvent(ctx->s_d2h, ev_run[nch - 1], 0);
+    if (out->hist_y) cudaMemcpyAsync(out->hist_y, d_hy, (size_t)scene->n_mons * OPTB_HIST_BINS * 8, cudaMemcpyDeviceToHost, ctx->s_d2h);
+    if (out->hist_yz) cudaMemcpyAsync(out->hist_yz, d_hyz, (size_t)scene->n_mons * OPTB_HIST_BINS * OPTB_HIST_BINS * 8, cudaMemcpyDeviceToHost, ctx->s_d2h);
+  }
+  cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_run);
+  cudaError_t e = cudaStreamSynchronize(ctx->s_d2h);
+  for (int c = 0; c < nch; c++) { cudaEventDestroy(ev_h2d[c]); cudaEventDestroy(ev_run[c]); cudaEventDestroy(ev_d2h[c]); }
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, -10, "pipelined trace", e);
+  if (chunk_overflow) return 1;
+  memcpy(ctx->h_counters, tot, sizeof tot);
+  if (out->counters) memcpy(out->counters, tot, sizeof tot);
+  return 0;
+}
+
 extern "C" int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
                                optb_result* out) {
   if (!ctx || !scene || !rays || !prm || !out) return -1;
+  if (!needs_wavefront(scene, prm) && scene->n_caps == 0 && rays->n >= (3ll << 20)) {
+    int rc = trace_host_pipelined(ctx, scene, rays, prm, out);
+    if (rc <= 0) return rc;  // 1 = a chunk outgrew its estimated share of the result capacity: one-shot path
+  }
   // The live ray set of a splitting scene is not known in advance: grow the workspace until it fits.
   for (int64_t factor = 4; factor <= 1024; factor *= 4) {
     int rc = trace_host_once(ctx, scene, rays, prm, out, factor);

@@ -129,3 +129,50 @@ def test_c5_ripa_7689_leaves(engine):
                              wavelengths=(p["wavelength"],), w0=p["R1w0"])
     got, _ = _both(engine, sc, arrs, limit=48, max_live=200_000)
     assert int(got["counters"][1]) > 40 * 2000
+
+
+def test_pipelined_host_trace_equals_device_trace(engine):
+    """optb_trace_host switches to the chunked three-stream pipeline above 3 Mi rays: same rows (as a set, keyed by
+    (root, monitor)), same histograms, same counters as one device-resident launch."""
+    import torch
+
+    import bench
+    from optable_b200 import _abi as A
+    from optable_b200.bundle import DeviceTrace
+    from optable_b200.flatten import rays_struct
+
+    n = 3_300_000
+    flat = bench.build_scene()
+    bundle = bench.make_bundle(n, 777)
+    dt = DeviceTrace(engine, flat, n, 2 * n, record_hist=True)
+    dt.run(bundle.to_torch(device="cuda:0"))
+    cnt = dt.counters()
+    nh = int(cnt[A.C_HITS])
+    host = {k: v.numpy() for k, v in bundle.to_torch(pin=True).items()}
+    host["length"] = None
+    rs = rays_struct({**{k: None for k in A.RAY_F64}, **host})
+    res = A.Result()
+    res.seg_capacity, res.hit_capacity = 0, 2 * n
+    out = {}
+    for k in dt.hit_columns:
+        out[k] = torch.empty(2 * n, dtype=dt.t[k].dtype).pin_memory()
+        setattr(res, k, out[k].data_ptr())
+    hy, hyz = torch.zeros(2, 30, dtype=torch.int64).pin_memory(), torch.zeros(2, 30, 30, dtype=torch.int64).pin_memory()
+    hc = torch.zeros(A.C_COUNT, dtype=torch.int64).pin_memory()
+    res.hist_y, res.hist_yz, res.counters = hy.data_ptr(), hyz.data_ptr(), hc.data_ptr()
+    engine.trace_host(dt.scene, rs, dt.prm, res)
+    assert int(hc[A.C_STATUS]) == 0
+    for c in (A.C_SEGMENTS, A.C_INTERACTIONS, A.C_HITS, A.C_DROPPED):
+        assert int(hc[c]) == int(cnt[c]), c
+    assert torch.equal(hy, dt.t["hist_y"].cpu()) and torch.equal(hyz, dt.t["hist_yz"].cpu())
+
+    def keyed(cols, rows):
+        key = cols["hit_root"][:rows].to(torch.int64) * 4 + cols["hit_monitor"][:rows].to(torch.int64)
+        order = torch.argsort(key)
+        return key[order], {k: v[:rows][order] for k, v in cols.items()}
+
+    ka, a = keyed({k: v.cpu() for k, v in dt.t.items() if k in dt.hit_columns}, nh)
+    kb, b = keyed(out, nh)
+    assert torch.equal(ka, kb)
+    for k in dt.hit_columns:
+        assert torch.equal(a[k], b[k]), k
