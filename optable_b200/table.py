@@ -141,6 +141,85 @@ class OpticalTable:
         self.rays.extend(trace_table(self, list(rays), perfomance_limit))
         return [r.copy() for r in self.rays]
 
+    # ---- callers of ray_tracing that the reference ships on the table (optical_table.py:211-422) ----------
+    def calculate_abcd_matrix(self, mon0: Monitor, mon1: Monitor, rays: List[Ray], disp=1e-5, rot=1e-5, debugaxs=None):
+        """Per-ray 2x2 ray-transfer matrix from `mon0` to `mon1` along the monitors' Y axis, by finite differences:
+        one nominal trace, one with every ray shifted by `disp` along mon0's tangent_Y, one with every (already
+        shifted) ray additionally turned by `rot` about mon0's tangent_Z through its recorded mon0 hit point.
+        Rays need distinct ids and must reach both monitors. Like the reference, `self.rays` and both monitors are
+        cleared before each trace, the shift is not undone before the rotation, and the pivot is the hit point in
+        monitor-local coordinates (optical_table.py:264-286). Returns an (N, 2, 2) array ordered by ray id."""
+        if debugaxs is not None:
+            raise NotImplementedError("rendering is out of scope of optable_b200")
+        assert len(rays) > 0, "No rays to trace in ABCD calculation."
+        ids = [r._id for r in rays]
+        assert len(set(ids)) == len(rays), "Redundant ray ids in ABCD calculation."
+        work = [rays[i].copy() for i in np.argsort(ids)]
+
+        def run(batch):
+            self.rays = []
+            mon0.clear()
+            mon1.clear()
+            self.ray_tracing(batch)
+            return mon1.get_yList(sort="ID"), mon1.get_tYList(sort="ID")
+
+        y0, t0 = run(work)
+        for mon, label in ((mon0, "mon0"), (mon1, "mon1")):
+            assert set(ids) == {r._id for r in mon.get_rays(sort="ID")}, f"Rays at {label} do not match the input rays."
+        pivots = mon0.get_PList(sort="ID")
+        shift, axis = mon0.tangent_Y * disp, mon0.tangent_Z
+        y1, t1 = run([r._Translate(shift) for r in work])
+        y2, t2 = run([r._RotAround(axis, pivots[k], rot) for k, r in enumerate(work)])
+        Ms = np.zeros((len(rays), 2, 2))
+        Ms[:, 0, 0], Ms[:, 1, 0] = (y1 - y0) / disp, (t1 - t0) / disp
+        Ms[:, 0, 1], Ms[:, 1, 1] = (y2 - y0) / rot, (t2 - t0) / rot
+        return Ms
+
+    @staticmethod
+    def calibrate_symmetric_4f(lens, rays: List[Ray], F10: float, F20: float, criterion: str = "M=-I", debugaxs=None,
+                               optimize=True, display_M=False):
+        """Symmetric 4f relay mon0 - F1 - lens - 2 F2 - lens (turned by pi) - F1 - mon1 built from two copies of
+        `lens`. With optimize=False: returns (Ms, yList, tYList) at (F10, F20). With optimize=True: Nelder-Mead
+        over (F1, F2) (xatol 1e-5, 50 iterations) on the chosen criterion -- "M=-I": mean |M + I|, "flat_field":
+        mean |d_s - d0| for d0 = 1.5, "min_stdtY": spread of the exit slopes -- and returns (F1, F2)
+        (optical_table.py:299-422)."""
+        if debugaxs is not None:
+            raise NotImplementedError("rendering is out of scope of optable_b200")
+
+        def simulate(F1, F2):
+            first = lens.copy()._Translate(np.array([F1, 0, 0]) - lens.origin)
+            second = lens.copy()._Translate(np.array([F1 + 2 * F2, 0, 0]) - lens.origin).RotZ(np.pi)
+            m0, m1 = Monitor(origin=[0, 0, 0], width=5, height=5), Monitor(origin=[2 * F1 + 2 * F2, 0, 0], width=5, height=5)
+            table = OpticalTable()
+            table.add_components([first, second])
+            table.add_monitors([m0, m1])
+            table.ray_tracing(rays)
+            y, ty = m1.get_yList(), m1.get_tYList()
+            Ms = table.calculate_abcd_matrix(m0, m1, rays)
+            if display_M:
+                for M in Ms:
+                    print(M)
+            return Ms, y, ty
+
+        def cost(F1, F2):
+            Ms, _, ty = simulate(F1, F2)
+            if criterion == "M=-I":
+                return float(np.mean([np.linalg.norm(M + np.eye(2)) for M in Ms]))
+            if criterion == "flat_field":
+                d0 = 1.5
+                return float(np.mean([abs((d0 * M[0, 0] - M[0, 1]) / (M[1, 1] - M[1, 0] * d0) - d0) for M in Ms]))
+            if criterion == "min_stdtY":
+                return float(np.std(ty))
+            raise ValueError(f"Unknown criterion: {criterion}")
+
+        if not optimize:
+            return simulate(F10, F20)
+        from scipy.optimize import minimize
+
+        res = minimize(lambda x: cost(x[0], x[1]), x0=[F10, F20], method="Nelder-Mead",
+                       options={"xatol": 1e-5, "maxiter": 50})
+        return tuple(res.x)
+
     def trace_bundle(self, bundle, perfomance_limit=None, **kw):
         """Tensor entry point: see optable_b200.bundle.trace_bundle."""
         from .bundle import trace_bundle

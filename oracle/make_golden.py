@@ -49,7 +49,33 @@ def make(name):
     return len(r["seg_root"]), len(r["hit_root"])
 
 
+def make_abcd():
+    """Fixture for the callers of ray_tracing (optical_table.py:211-422): the reference's own
+    calculate_abcd_matrix and calibrate_symmetric_4f(optimize=False) on the LENS-9 asphere with 7 id'd rays."""
+    ref = RH.load_reference()
+    lens = scenes.asphere_lens9(ref, [43.17, 0, 0])
+    rays = scenes.abcd_rays(ref)
+    F1, F2 = 46.52, 43.48
+    # the body of calibrate_symmetric_4f.simulate (optical_table.py:328-347); the method itself cannot run
+    # headless with optimize=False because it ends in table.render(type=None), which raises
+    l0 = lens.copy()._Translate(np.array([F1, 0, 0]) - lens.origin)
+    l1 = lens.copy()._Translate(np.array([F1 + 2 * F2, 0, 0]) - lens.origin).RotZ(np.pi)
+    m0, m1 = ref.Monitor(origin=[0, 0, 0], width=5, height=5), ref.Monitor(origin=[2 * F1 + 2 * F2, 0, 0], width=5, height=5)
+    table = ref.OpticalTable()
+    table.add_components([l0, l1])
+    table.add_monitors([m0, m1])
+    table.ray_tracing(rays)
+    y, ty = m1.get_yList(), m1.get_tYList()
+    Ms = table.calculate_abcd_matrix(m0, m1, rays)
+    np.savez_compressed(os.path.join(OUT, "abcd_4f.npz"), Ms=np.asarray(Ms), yList=np.asarray(y), tYList=np.asarray(ty),
+                        F=np.array([F1, F2]))
+    return np.asarray(Ms)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["abcd"]:
+        print(make_abcd()[:2])
+        sys.exit(0)
     for name in (sys.argv[1:] or scenes.REGISTRY):
         nseg, nhit = make(name)
         print(f"{name:20s} segments={nseg} hits={nhit}")

@@ -117,6 +117,12 @@ def telescope_4f(ns, n_rays=7, disc=True):
     return Scene([l0, l1], rays, [mon0, mon1])
 
 
+def abcd_rays(ns, N=3, D=0.6):
+    """examples/calibrate_4f.py:184-191: 2N+1 Gaussian rays with explicit integer ids."""
+    return [ns.Ray([-10, i * D, 0], [1, 0, 0], wavelength=780e-7, w0=61e-4, id=int(i + N)).Propagate(-10)
+            for i in np.arange(-N, N + 1)]
+
+
 def exact_asphere(ns):
     """ASphericExactSphericalLens (component_group.py:1065-1082) with tilted rays."""
     lens = ns.ASphericExactSphericalLens([10, 0, 0], EFL=20.0, CT=0.6, diameter=5.0, n=1.5)

@@ -92,3 +92,23 @@ def test_second_call_extends_and_bundle_entry():
     t2.add_monitors(sc2.monitors)
     res = t2.trace_bundle(RayBundle.collimated_disc(50_000), record_hist=True)
     assert int(res["counters"][1]) == 4 * 50_000 and int(res["hist_y"].sum()) == len(res["hit_monitor"])
+
+
+def test_abcd_matrix_and_4f_calibration_callers():
+    """The callers of ray_tracing the reference ships on OpticalTable (optical_table.py:211-422) on the GPU back
+    end: finite-difference ABCD matrices and the symmetric-4f simulate step against the reference's own values.
+    The matrices are differences of traced positions divided by 1e-5, so 1e-9 parity of the traces gives ~1e-4
+    absolute on the entries; the fixture's entries are O(1) (and O(100) for B)."""
+    import os
+
+    z = np.load(os.path.join(golden_io.GOLDEN_DIR, "abcd_4f.npz"))
+    lens = scenes.asphere_lens9(ob, [43.17, 0, 0])
+    rays = scenes.abcd_rays(ob)
+    F1, F2 = z["F"]
+    Ms, y, ty = ob.OpticalTable.calibrate_symmetric_4f(lens, rays, F10=F1, F20=F2, optimize=False)
+    np.testing.assert_allclose(y, z["yList"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(ty, z["tYList"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(Ms, z["Ms"], rtol=1e-5, atol=2e-4)
+    assert Ms.shape == (7, 2, 2) and abs(Ms[3, 0, 0] + 1) < 0.2   # a 4f relay images with magnification about -1
+    F = ob.OpticalTable.calibrate_symmetric_4f(lens, rays[2:5], F10=F1, F20=F2, criterion="min_stdtY", optimize=True)
+    assert len(F) == 2 and all(np.isfinite(F)) and abs(F[0] - F1) < 5
