@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OPTB_ABI_VERSION 5
+#define OPTB_ABI_VERSION 6
 
 /* ---- scene node table ------------------------------------------------------
  * The component tree (OpticalTable.components, groups nested to any depth) is
@@ -91,6 +91,8 @@ enum {
   OPTB_NI_AUX = 7,    /* offset (in doubles) into aux pool, or asphere form       */
   OPTB_NI_ROCKIND = 8,
   OPTB_NI_LEAF = 9,   /* dense leaf number (-1 for groups); reported as hit index */
+  OPTB_NI_ORTHO = 10, /* 1: Tinv is orthonormal to 1e-14, so |Tinv d| = 1 to rounding and the device skips the
+                         re-normalisations of ray_to_local/lab_coordinates (a 1e-16 relative difference)      */
   OPTB_NI_STRIDE = 12
 };
 
@@ -124,7 +126,7 @@ enum { OPTB_MAT_CONST = 0, OPTB_MAT_SELLMEIER = 1, OPTB_MF_STRIDE = 8 };
  * rotated monitors); the histograms reproduce exactly that.                               */
 enum {
   OPTB_MON_ORIGIN = 0, OPTB_MON_TINV = 3, OPTB_MON_HW = 12, OPTB_MON_HH = 13,
-  OPTB_MON_TY = 14, OPTB_MON_TZ = 17, OPTB_MON_STRIDE = 20
+  OPTB_MON_TY = 14, OPTB_MON_TZ = 17, OPTB_MON_ORTHO = 20 /* 1.0 when Tinv is orthonormal */, OPTB_MON_STRIDE = 24
 };
 enum { OPTB_HIST_BINS = 30 };
 

@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes and constants against the compiled library."""
 import ctypes as C
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # geometry kinds
 G_GROUP, G_CIRCLE, G_RECT, G_SPHERE, G_ASPHERE, G_CYL, G_POLY2D, G_POLY3D, G_CSG = range(9)
@@ -11,13 +11,13 @@ I_NONE, I_MIRROR, I_REFRACT, I_THINLENS, I_ABSORB = range(5)
 ROC_INF, ROC_CONST, ROC_ASPHERE_FD = range(3)
 ASPH_PARAMETRIC, ASPH_EXACT_SPH = 1, 2
 
-NI_GEOM, NI_INTER, NI_SKIP, NI_AABB, NI_MAT1, NI_MAT2, NI_CAPSLOT, NI_AUX, NI_ROCKIND, NI_LEAF = range(10)
+NI_GEOM, NI_INTER, NI_SKIP, NI_AABB, NI_MAT1, NI_MAT2, NI_CAPSLOT, NI_AUX, NI_ROCKIND, NI_LEAF, NI_ORTHO = range(11)
 NI_STRIDE = 12
 NF_AABB, NF_ORIGIN, NF_TINV, NF_T, NF_P = 0, 6, 9, 18, 27
 NF_REFL, NF_TRANS, NF_FOCAL, NF_ROC, NF_CAPMAX, NF_STRIDE = 35, 36, 37, 38, 39, 40
 POLY_HEADER = 19
 MAT_CONST, MAT_SELLMEIER, MF_STRIDE = 0, 1, 8
-MON_ORIGIN, MON_TINV, MON_HW, MON_HH, MON_TY, MON_TZ, MON_STRIDE = 0, 3, 12, 13, 14, 17, 20
+MON_ORIGIN, MON_TINV, MON_HW, MON_HH, MON_TY, MON_TZ, MON_ORTHO, MON_STRIDE = 0, 3, 12, 13, 14, 17, 20, 24
 HIST_BINS = 30
 
 RF_ALIVE, RF_HASQ = 1, 2

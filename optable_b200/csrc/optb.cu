@@ -165,8 +165,8 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
   for (int m = 0; m < sv.n_mons; m++) {
     const double* mf = sv.mon + m * OPTB_MON_STRIDE;
     double ox, oy, oz, dx, dy, dz;
-    to_local(mf + OPTB_MON_ORIGIN, mf + OPTB_MON_TINV, r, ox, oy, oz, dx, dy, dz);
-    if (dx == 0.0) continue;
+    to_local(mf + OPTB_MON_ORIGIN, mf + OPTB_MON_TINV, r, mf[OPTB_MON_ORTHO] != 0.0, ox, oy, oz, dx, dy, dz);
+    if (!((ox < 0.0 && dx > 0.0) || (ox > 0.0 && dx < 0.0))) continue;  // t = -ox/dx >= 1e-9 needs opposite signs
     double t = -ox / dx;
     if (!(t >= 1e-9) || t > seg_len) continue;
     double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
@@ -225,7 +225,7 @@ struct HitSearch {
 
   OPTB_DEV void test_leaf(int i, const int32_t* __restrict__ ni, const double* __restrict__ nf) {
     double ox, oy, oz, dx, dy, dz;
-    to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);
+    to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
     tests++;
     const int slot = ni[OPTB_NI_CAPSLOT];
     // a capped surface counts every geometric hit, closest or not (optical_component.py:359-362): no early exit
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
           if (!hit) continue;
           c_inter++;
           double ox, oy, oz, dx, dy, dz;
-          to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);
+          to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
           Children ch;
           interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch);
           for (int k = 0; k < ch.n; k++) {
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
       if (!hit) { nch = 0; break; }
       c_inter++;
       double ox, oy, oz, dx, dy, dz;
-      to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ox, oy, oz, dx, dy, dz);
+      to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
       interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch);
       nch = ch.n;
       if (nch == 1 && solo && (a.chain_len == 0 || chained + 1 < a.chain_len)) {

@@ -46,17 +46,19 @@ OPTB_DEV double dot3(double ax, double ay, double az, double bx, double by, doub
 }
 
 // ray_to_local_coordinates optical_component.py:106-111 (+ direction setter ray.py:115-119)
-OPTB_DEV void to_local(const double* __restrict__ c, const double* __restrict__ Ti, const Ray& r,
+OPTB_DEV void to_local(const double* __restrict__ c, const double* __restrict__ Ti, const Ray& r, bool ortho,
                        double& ox, double& oy, double& oz, double& dx, double& dy, double& dz) {
   double vx = r.ox - c[0], vy = r.oy - c[1], vz = r.oz - c[2];
   ox = dot3(Ti[0], Ti[1], Ti[2], vx, vy, vz);
   oy = dot3(Ti[3], Ti[4], Ti[5], vx, vy, vz);
   oz = dot3(Ti[6], Ti[7], Ti[8], vx, vy, vz);
-  double ex = dot3(Ti[0], Ti[1], Ti[2], r.dx, r.dy, r.dz);
-  double ey = dot3(Ti[3], Ti[4], Ti[5], r.dx, r.dy, r.dz);
-  double ez = dot3(Ti[6], Ti[7], Ti[8], r.dx, r.dy, r.dz);
-  double rn = rsqrt(dot3(ex, ey, ez, ex, ey, ez));
-  dx = ex * rn; dy = ey * rn; dz = ez * rn;
+  dx = dot3(Ti[0], Ti[1], Ti[2], r.dx, r.dy, r.dz);
+  dy = dot3(Ti[3], Ti[4], Ti[5], r.dx, r.dy, r.dz);
+  dz = dot3(Ti[6], Ti[7], Ti[8], r.dx, r.dy, r.dz);
+  if (!ortho) {  // an orthonormal frame keeps |d| = 1 to rounding: the reference's re-normalisation is a no-op
+    double rn = rsqrt(dot3(dx, dy, dz, dx, dy, dz));
+    dx *= rn; dy *= rn; dz *= rn;
+  }
 }
 
 // solve_ray_bboxes_intersections solver.py:5-48, one box
@@ -229,6 +231,26 @@ struct AsphF {
     }
     return fma(R, sqrt(fma(k1, r2, 1.0)) - 1.0, Px);
   }
+  // Same sign as operator()(t) (NaN where the reference's f is NaN), without the square root:
+  // g = sgn * (A s + B) with s = sqrt(s2) >= 0; when A and B disagree in sign the comparison is done on squares.
+  OPTB_DEV double sign(double t) const {
+    double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+    double r2 = fma(Py, Py, Pz * Pz);
+    double A, B, s2;
+    if (form == OPTB_ASPH_PARAMETRIC) {
+      s2 = fma(-k1, r2, 1.0);
+      A = fma(r2 * r2, fma(r2, fma(r2, a8, a6), a4), Px) * R;
+      B = r2 + A;
+    } else {
+      s2 = fma(k1, r2, 1.0);
+      A = R; B = Px - R;
+    }
+    double v;
+    if ((A >= 0.0) == (B >= 0.0)) v = A + B;
+    else { double d = fma(A * A, s2, -B * B); v = (A >= 0.0) ? d : -d; }
+    if (!(s2 >= 0.0)) v = NAN;
+    return sgn * v;
+  }
 };
 
 template <class F>
@@ -287,7 +309,9 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
   const double* p = nf + OPTB_NF_P;
   if (g == OPTB_G_CIRCLE || g == OPTB_G_RECT || g == OPTB_G_POLY2D || g == OPTB_G_CSG) {
     // planar branch :165-196: plane x = 0
-    if (dx == 0.0) return -1.0;          // parallel: miss, or t = 0 which |t| < EPS rejects
+    // t = -ox/dx must be >= 1e-9: origin and direction on opposite sides of the plane (also covers dx == 0,
+    // which the reference resolves to a miss or to t = 0 < EPS); decided before paying for the division
+    if (!((ox < 0.0 && dx > 0.0) || (ox > 0.0 && dx < 0.0))) return -1.0;
     double t = -ox / dx;
     if (!(t >= 1e-9) || t > len) return -1.0;  // |t|<EPS, t<0, t>length, NaN
     double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
@@ -332,32 +356,32 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
     // sub-interval.
     const AsphF f(ni[OPTB_NI_AUX], p + 1, ox, oy, oz, dx, dy, dz);
     const bool asc = (b >= a);
-    double ta = a, fa = f(a), best = -1.0;
+    double ta = a, fa = f.sign(a), best = -1.0;   // the scan only needs signs
     int i = 1;
     while (i < 10) {
       double tb = ta, fb = fa;
       bool sc = false;
       for (; i < 10; i++) {
-        tb = sample_t(i, a, b, step); fb = f(tb);
+        tb = sample_t(i, a, b, step); fb = f.sign(tb);
         if (fa * fb < 0) { sc = true; break; }
         ta = tb; fa = fb;
       }
       if (!sc) break;
       bool solve = true;
-      double lo = ta, flo = fa;
+      double lo = ta;
       if (asc) {
         if (tb <= 1e-9 || ta > len) solve = false;  // every root in here fails t >= EPS (or t <= length)
         else if (ta < 1e-9) {
           // The sub-interval straddles the admissibility threshold (the usual case right after leaving this
           // very surface: the root is the self-intersection at t ~ 0). One sample at t = EPS tells on which
           // side the root lies; below it the reference finds it with brentq and then filters it out.
-          double fe = f(1e-9);
+          double fe = f.sign(1e-9);
           if (fa * fe < 0) solve = false;
-          else if (fe * fb < 0) { lo = 1e-9; flo = fe; }
+          else if (fe * fb < 0) lo = 1e-9;
         }
       }
       if (solve) {
-        double r = brentq(f, lo, tb, flo, fb);
+        double r = brentq(f, lo, tb, f(lo), f(tb));
         if (r >= 1e-9 && r <= len) {
           double Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
           if (sqrt(fma(Py, Py, Pz * Pz)) <= p[0] + 1e-12) {   // ASphere.within_boundary
@@ -487,9 +511,12 @@ struct Children {
 };
 
 // local child direction -> lab (ray_to_lab_coordinates :119-124; both normalisations)
-OPTB_DEV void dir_to_lab(const double* __restrict__ T, double lx, double ly, double lz, double& gx, double& gy, double& gz) {
-  double rn = rsqrt(dot3(lx, ly, lz, lx, ly, lz));
-  lx *= rn; ly *= rn; lz *= rn;
+OPTB_DEV void dir_to_lab(const double* __restrict__ T, bool ortho, double lx, double ly, double lz,
+                         double& gx, double& gy, double& gz) {
+  if (!ortho) {  // for an orthonormal T one normalisation (after the rotation) is the same as the reference's two
+    double rn = rsqrt(dot3(lx, ly, lz, lx, ly, lz));
+    lx *= rn; ly *= rn; lz *= rn;
+  }
   double ex = dot3(T[0], T[1], T[2], lx, ly, lz);
   double ey = dot3(T[3], T[4], T[5], lx, ly, lz);
   double ez = dot3(T[6], T[7], T[8], lx, ly, lz);
@@ -503,6 +530,7 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
                        double t, Children& ch) {
   const double* T = nf + OPTB_NF_T;
   const double* c = nf + OPTB_NF_ORIGIN;
+  const bool ortho = ni[OPTB_NI_ORTHO] != 0;
   double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
   ch.n = 0;
   ch.ox = dot3(T[0], T[1], T[2], Px, Py, Pz) + c[0];
@@ -521,7 +549,7 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
       cdiv(q1r, q1i, 1.0 - q1r / f, -(q1i / f), qre, qim);
     }
     double inv_f = 1.0 / f;
-    dir_to_lab(T, dx - Px * inv_f, dy - Py * inv_f, dz - Pz * inv_f, ch.dx[0], ch.dy[0], ch.dz[0]);
+    dir_to_lab(T, ortho, dx - Px * inv_f, dy - Py * inv_f, dz - Pz * inv_f, ch.dx[0], ch.dy[0], ch.dz[0]);
     ch.I[0] = ray.I * trans; ch.qre[0] = qre; ch.qim[0] = qim; ch.nmed[0] = ray.n;
     ch.pl = ray.pl;  // the thin lens leaves _pathlength untouched
     ch.n = 1;
@@ -534,11 +562,11 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
     double qre = ray.qre + t, qim = ray.qim;
     int k = 0;
     if (refl > 0) {
-      dir_to_lab(T, fma(-2 * dn, nx, dx), fma(-2 * dn, ny, dy), fma(-2 * dn, nz, dz), ch.dx[k], ch.dy[k], ch.dz[k]);
+      dir_to_lab(T, ortho, fma(-2 * dn, nx, dx), fma(-2 * dn, ny, dy), fma(-2 * dn, nz, dz), ch.dx[k], ch.dy[k], ch.dz[k]);
       ch.I[k] = ray.I * refl; ch.qre[k] = qre; ch.qim[k] = qim; ch.nmed[k] = ray.n; k++;
     }
     if (trans > 0) {
-      dir_to_lab(T, dx, dy, dz, ch.dx[k], ch.dy[k], ch.dz[k]);
+      dir_to_lab(T, ortho, dx, dy, dz, ch.dx[k], ch.dy[k], ch.dz[k]);
       ch.I[k] = ray.I * trans; ch.qre[k] = qre; ch.qim[k] = qim; ch.nmed[k] = ray.n; k++;
     }
     ch.n = k;
@@ -555,19 +583,23 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
   double nin, nout;
   if (dn < 0) { nin = n1; nout = n2; }
   else { nin = n2; nout = n1; ROC = -ROC; }
-  double qtr = 0, qti = 0, qrr = 0, qri = 0;
-  if (hasq) {
-    double qr = ray.qre + t, qi = ray.qim;
-    double Cc = (nin - nout) / (ROC * nout), D = nin / nout;
-    cdiv(qr, qi, fma(Cc, qr, D), Cc * qi, qtr, qti);
-    double C2 = 2.0 / ROC;
-    cdiv(qr, qi, fma(C2, qr, 1.0), C2 * qi, qrr, qri);
-  }
   double rtx = fma(-dn, nx, dx), rty = fma(-dn, ny, dy), rtz = fma(-dn, nz, dz);
   double sgn = dn > 0 ? 1.0 : -1.0;
   double cos_i = fmin(fmax(dn, -1.0), 1.0);
   double sin_i = sqrt(1.0 - cos_i * cos_i);
   double sin_t = (nin * sin_i) / nout;
+  double qtr = 0, qti = 0, qrr = 0, qri = 0;
+  if (hasq) {  // ABCD of the refraction / of the reflection (:648-666); each only when a child will carry it
+    double qr = ray.qre + t, qi = ray.qim;
+    if (sin_t < 1 && trans > 0) {
+      double Cc = (nin - nout) / (ROC * nout), D = nin / nout;
+      cdiv(qr, qi, fma(Cc, qr, D), Cc * qi, qtr, qti);
+    }
+    if (!(sin_t < 1) || refl > 0) {
+      double C2 = 2.0 / ROC;
+      cdiv(qr, qi, fma(C2, qr, 1.0), C2 * qi, qrr, qri);
+    }
+  }
   // reflected direction d + 2 cos_i (-n)
   double rfx = fma(-2 * cos_i, nx, dx), rfy = fma(-2 * cos_i, ny, dy), rfz = fma(-2 * cos_i, nz, dz);
   int k = 0;
@@ -575,18 +607,18 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
     if (trans > 0) {
       double cos_t = sqrt(1.0 - sin_t * sin_t);
       double kk = nin / nout, cs = cos_t * sgn;
-      dir_to_lab(T, fma(kk, rtx, cs * nx), fma(kk, rty, cs * ny), fma(kk, rtz, cs * nz), ch.dx[k], ch.dy[k], ch.dz[k]);
+      dir_to_lab(T, ortho, fma(kk, rtx, cs * nx), fma(kk, rty, cs * ny), fma(kk, rtz, cs * nz), ch.dx[k], ch.dy[k], ch.dz[k]);
       ch.I[k] = ray.I * trans; ch.qre[k] = qtr; ch.qim[k] = qti; ch.nmed[k] = nout; k++;
     }
   } else {  // total internal reflection (also taken when sin_t is NaN, as `sin_t < 1` is False)
-    dir_to_lab(T, rfx, rfy, rfz, ch.dx[k], ch.dy[k], ch.dz[k]);
+    dir_to_lab(T, ortho, rfx, rfy, rfz, ch.dx[k], ch.dy[k], ch.dz[k]);
     ch.I[k] = ray.I; ch.qre[k] = qrr; ch.qim[k] = qri; ch.nmed[k] = ray.n; k++;
   }
   if (refl > 0) {
     if (k == 1 && !(sin_t < 1)) {  // TIR + reflectivity: same direction twice
       ch.dx[1] = ch.dx[0]; ch.dy[1] = ch.dy[0]; ch.dz[1] = ch.dz[0];
     } else {
-      dir_to_lab(T, rfx, rfy, rfz, ch.dx[k], ch.dy[k], ch.dz[k]);
+      dir_to_lab(T, ortho, rfx, rfy, rfz, ch.dx[k], ch.dy[k], ch.dz[k]);
     }
     ch.I[k] = ray.I * refl; ch.qre[k] = qrr; ch.qim[k] = qri; ch.nmed[k] = ray.n; k++;
   }

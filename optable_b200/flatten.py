@@ -28,6 +28,10 @@ class FlattenError(NotImplementedError):
     """The scene uses a construct the device tables cannot express (no CPU fallback exists)."""
 
 
+def _orthonormal(M) -> bool:
+    return bool(np.abs(M @ M.T - np.identity(3)).max() < 1e-14)
+
+
 def _mro_names(obj):
     return {k.__name__ for k in type(obj).__mro__}
 
@@ -133,6 +137,7 @@ class FlatScene:
             T = np.asarray(m.transform_matrix, dtype=np.float64)
             self.mon_f[k, A.MON_ORIGIN:A.MON_ORIGIN + 3] = np.asarray(m.origin, dtype=np.float64)
             self.mon_f[k, A.MON_TINV:A.MON_TINV + 9] = np.linalg.inv(T).reshape(-1)
+            self.mon_f[k, A.MON_ORTHO] = float(_orthonormal(np.linalg.inv(T)))
             self.mon_f[k, A.MON_HW] = m.width / 2
             self.mon_f[k, A.MON_HH] = m.height / 2
             self.mon_f[k, A.MON_TY:A.MON_TY + 3] = T @ np.array([0.0, 1.0, 0.0])
@@ -243,8 +248,10 @@ class FlatScene:
         self.leaves.append(comp)
         T = np.asarray(comp.transform_matrix, dtype=np.float64)
         nf[A.NF_ORIGIN:A.NF_ORIGIN + 3] = [float(v) for v in comp.origin]
-        nf[A.NF_TINV:A.NF_TINV + 9] = np.linalg.inv(T).reshape(-1).tolist()
+        Tinv = np.linalg.inv(T)
+        nf[A.NF_TINV:A.NF_TINV + 9] = Tinv.reshape(-1).tolist()
         nf[A.NF_T:A.NF_T + 9] = T.reshape(-1).tolist()
+        ni[A.NI_ORTHO] = int(_orthonormal(Tinv))
         if in_group:
             nf[A.NF_AABB:A.NF_AABB + 6] = [float(v) for v in comp.bbox]
         self._geometry(comp.surface, sname, ni, nf)
