@@ -351,22 +351,26 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
   const double step = (b - a) / 9.0;
   // roots found by the sign scan, ascending in t (sub-intervals are visited in order)
   if (g == OPTB_G_ASPHERE) {
-    // Scan first, solve after: every lane walks the 10 samples in lock-step and leaves the inner loop at its
-    // own sign change; the (expensive) root solve then runs once for the whole warp instead of once per
-    // sub-interval.
+    // Scan first, solve after: the (expensive) root solve runs once for the whole warp instead of once per
+    // sub-interval (lane efficiency 21 -> 31 of 32).
     const AsphF f(ni[OPTB_NI_AUX], p + 1, ox, oy, oz, dx, dy, dz);
     const bool asc = (b >= a);
-    double ta = a, fa = f.sign(a), best = -1.0;   // the scan only needs signs
-    int i = 1;
-    while (i < 10) {
-      double tb = ta, fb = fa;
-      bool sc = false;
-      for (; i < 10; i++) {
-        tb = sample_t(i, a, b, step); fb = f.sign(tb);
-        if (fa * fb < 0) { sc = true; break; }
-        ta = tb; fa = fb;
-      }
-      if (!sc) break;
+    // All ten sample signs first, as two bit masks: the evaluations are independent, so the fp64 pipe sees ten
+    // interleaved dependency chains instead of one (and nothing but 20 bits stays live afterwards).
+    unsigned pos = 0u, neg = 0u;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      const double v = f.sign(sample_t(i, a, b, step));
+      pos |= (v > 0.0 ? 1u : 0u) << i;
+      neg |= (v < 0.0 ? 1u : 0u) << i;
+    }
+    unsigned chg = ((pos & (neg >> 1)) | (neg & (pos >> 1))) & 0x1ffu;  // bit i: f(ts_i) * f(ts_i+1) < 0
+    double best = -1.0;
+    while (chg) {
+      const int i = __ffs(chg) - 1;
+      chg &= chg - 1u;
+      const double ta = sample_t(i, a, b, step), tb = sample_t(i + 1, a, b, step);
+      const bool fa_pos = (pos >> i) & 1u;
       bool solve = true;
       double lo = ta;
       if (asc) {
@@ -375,9 +379,9 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
           // The sub-interval straddles the admissibility threshold (the usual case right after leaving this
           // very surface: the root is the self-intersection at t ~ 0). One sample at t = EPS tells on which
           // side the root lies; below it the reference finds it with brentq and then filters it out.
-          double fe = f.sign(1e-9);
-          if (fa * fe < 0) solve = false;
-          else if (fe * fb < 0) lo = 1e-9;
+          const double fe = f.sign(1e-9);
+          if (fa_pos ? fe < 0.0 : fe > 0.0) solve = false;       // f(ta) * f(EPS) < 0
+          else if (fa_pos ? fe > 0.0 : fe < 0.0) lo = 1e-9;      // f(EPS) * f(tb) < 0
         }
       }
       if (solve) {
@@ -390,7 +394,6 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
           }
         }
       }
-      ta = tb; fa = fb; i++;
     }
     return best;
   }
