@@ -90,7 +90,7 @@ def _workloads():
         "c2_4f_telescope": (c2_scene, c2_rays, dict(max_trace_num=2000, rays=10_000_000, rows_per_ray=2)),
         "c3_doublets_16wl": (c3_scene, c3_rays, dict(max_trace_num=2000, rays=10_000_000, rows_per_ray=1)),
         "c4_cavity_4000": (c4_scene, c4_rays, dict(max_trace_num=4001, rays=1_000_000, rows_per_ray=0)),
-        "c5_ripa_64": (c5_scene, c5_rays, dict(max_trace_num=64, rays=1_000_000, rows_per_ray=64)),
+        "c5_ripa_64": (c5_scene, c5_rays, dict(max_trace_num=64, rays=1_000_000, rows_per_ray=64, max_live=8)),
     }
 
 
@@ -211,8 +211,10 @@ def run_cuda(args):
             dist.all_reduce(dt.t["hist_y"])
             dist.all_reduce(dt.t["hist_yz"])
 
+    live = wprm.get("max_live", 0) * n or None  # live-ray budget of the wavefront (splitting scenes)
+
     def step():
-        dt.run(rays_dev)
+        dt.run(rays_dev, live)
         merge_monitors()
 
     for _ in range(args.warmup):
@@ -234,7 +236,7 @@ def run_cuda(args):
     for k in range(args.steps):
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record(stream)
-        dt.run(rays_dev)
+        dt.run(rays_dev, live)
         k1.record(stream)
         merge_monitors()
         ev[k + 1].record(stream)
@@ -258,6 +260,33 @@ def run_cuda(args):
     value = inter_all / (ms_per_step * 1e-3)
 
     # ---- end to end through the C ABI with HOST buffers (optb_trace_host): H2D rays + D2H monitor rows ----
+    hit_columns, hit_dtypes, row_bytes = dt.hit_columns, {k: dt.t[k].dtype for k in dt.hit_columns}, dt.hit_row_bytes()
+    hist_shapes = (tuple(dt.t["hist_y"].shape), tuple(dt.t["hist_yz"].shape))
+    for k in list(dt.t):  # the device-resident result buffers are not needed any more: give the memory back
+        if k.startswith(("hit_", "seg_")):
+            del dt.t[k]
+    del rays_dev
+    engine._workspace = None
+    torch.cuda.empty_cache()
+    if args.e2e_steps <= 0:
+        e2e_value, h2d, d2h, e2e_steps = None, 0, 0, 0
+    else:
+        e2e_value, h2d, d2h, e2e_steps = run_e2e(args, engine, dt, bundle, n, hit_cap, hit_columns, hit_dtypes, row_bytes,
+                                                 hist_shapes, inter_per_step, hits_per_step, inter_all, world, dev)
+    finish(args, engine, flat, world, rank, n, inter_per_step, hits_per_step, launches_per_step, ms_per_step, trace_ms,
+           value, clocks, e2e_value, h2d, d2h, e2e_steps)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, engine, dt, bundle, n, hit_cap, hit_columns, hit_dtypes, row_bytes, hist_shapes, inter_per_step,
+            hits_per_step, inter_all, world, dev):
+    import torch
+    import torch.distributed as dist
+
+    from optable_b200 import _abi as A
+    from optable_b200.flatten import rays_struct
+
     host = bundle.to_torch(pin=True)
     host_np = {k: v.numpy() for k, v in host.items()}
     host_np["length"] = None
@@ -266,14 +295,15 @@ def run_cuda(args):
     res = A.Result()
     res.seg_capacity, res.hit_capacity = 0, hit_cap
     host_out = {}
-    for k in dt.hit_columns:
-        host_out[k] = torch.empty(hit_cap, dtype=dt.t[k].dtype).pin_memory()
+    for k in hit_columns:
+        host_out[k] = torch.empty(hit_cap, dtype=hit_dtypes[k]).pin_memory()
         setattr(res, k, host_out[k].data_ptr())
-    hy = torch.zeros_like(dt.t["hist_y"], device="cpu").pin_memory()
-    hyz = torch.zeros_like(dt.t["hist_yz"], device="cpu").pin_memory()
+    hy = torch.zeros(hist_shapes[0], dtype=torch.int64).pin_memory()
+    hyz = torch.zeros(hist_shapes[1], dtype=torch.int64).pin_memory()
     hc = torch.zeros(A.C_COUNT, dtype=torch.int64).pin_memory()
     res.hist_y, res.hist_yz, res.counters = hy.data_ptr(), hyz.data_ptr(), hc.data_ptr()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    wprm = _workloads()[args.workload][2]
     for _ in range(2):
         engine.trace_host(dt.scene, rs, dt.prm, res)
     torch.cuda.synchronize()
@@ -291,11 +321,13 @@ def run_cuda(args):
     assert int(hc[A.C_STATUS]) == 0 and int(hc[A.C_INTERACTIONS]) == inter_per_step, (hc.tolist(), inter_per_step)
     e2e_value = inter_all * e2e_steps / e2e_s
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = hits_per_step * dt.hit_row_bytes() + hy.numel() * 8 + hyz.numel() * 8 + A.C_COUNT * 8
+    d2h = hits_per_step * row_bytes + hy.numel() * 8 + hyz.numel() * 8 + A.C_COUNT * 8
+    return e2e_value, h2d, d2h, e2e_steps
 
+
+def finish(args, engine, flat, world, rank, n, inter_per_step, hits_per_step, launches_per_step, ms_per_step, trace_ms,
+           value, clocks, e2e_value, h2d, d2h, e2e_steps):
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     peaks = {}
     try:
@@ -331,8 +363,6 @@ def run_cuda(args):
                              "sample": f"first {args.cpu_rays} rays of the same batch ({cpu_inter} interactions in {cpu_dt:.2f} s), "
                                        f"oracle/optb_oracle.c with {threads} threads"}}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

@@ -203,7 +203,7 @@ class Engine:
         n = int(rs.n)
         splitting = scene.flat.max_children > 1 or params.chain_len > 0 or scene.flat.n_capslots > 0
         live = 0 if not splitting else int(max_live if max_live is not None else max(4 * n, 1024))
-        if scene.flat.n_capslots:  # family-serial mode: total FIFO entries over all families
+        if scene.flat.n_capslots and not params.caps_slack:  # family-serial mode: total FIFO entries over all families
             live = max(live, min(64 * max(n, 16), n * (int(params.max_trace_num) + 2)))
         nbytes = lib().optb_workspace_bytes(scene._h, n, live)
         ws = self._ws(nbytes)

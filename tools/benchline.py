@@ -12,6 +12,6 @@ if not lines:
 d = json.loads(lines[-1])
 cfg = d.get("config", {})
 print(" ".join(sys.argv[1:]), "| value %.4e" % d["value"], "ms/step %.3f" % d["ms_per_step"],
-      "e2e %.4e" % d.get("e2e", {}).get("value", 0), "launches", d.get("gpu_launches"),
+      "e2e %.4e" % (d.get("e2e", {}).get("value") or 0), "launches", d.get("gpu_launches"),
       "inter/step", cfg.get("interactions_per_step_per_gpu"), "clk", d.get("clocks", {}).get("sm_mhz"),
       "cpu %.3e" % d.get("cpu_baseline", {}).get("value", 0))
