@@ -179,6 +179,18 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank (and the pinned host buffers it allocates next) to the CPUs closest to its GPU, so that the
+    host<->device copies of eight ranks do not all cross one socket link. Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -192,6 +204,7 @@ def run_cuda(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = f"cuda:{local}"
