@@ -360,6 +360,10 @@ def finish(args, engine, flat, world, rank, n, inter_per_step, hits_per_step, la
         af = FLOPS_PER_INTERACTION * inter_per_step / (trace_ms * 1e-3) / 1e12
         roofline_fp64.update({"achieved": af, "frac": af / fp64_peak})
     threads = os.cpu_count() or 1
+    try:
+        os.sched_setaffinity(0, range(threads))  # the CPU baseline gets every host core again
+    except Exception:
+        pass
     cpu_val, cpu_inter, cpu_dt = cpu_arm(flat, args.cpu_rays, threads, workload=args.workload)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

@@ -227,16 +227,17 @@ class OpticalTable:
         return trace_bundle(self, bundle, perfomance_limit, **kw)
 
 
-def install(reference_module):
+def install(reference_module, engine=None):
     """Swap the back end under the reference package's own classes: `reference_module.OpticalTable.ray_tracing`
-    becomes a call into liboptb.so (SURVEY 8b "install mechanism"). Returns the original method."""
+    becomes a call into liboptb.so (SURVEY 8b "install mechanism"). Returns the original method (assign it back to
+    undo). `engine` defaults to the CUDA engine of the current device."""
     original = reference_module.OpticalTable.ray_tracing
     ray_cls = reference_module.Ray
 
     def ray_tracing(self, rays, perfomance_limit=None):
         if isinstance(rays, ray_cls):
             rays = [rays]
-        self.rays.extend(trace_table(self, list(rays), perfomance_limit))
+        self.rays.extend(trace_table(self, list(rays), perfomance_limit, engine=engine))
         return _copy.deepcopy(self.rays)
 
     reference_module.OpticalTable.ray_tracing = ray_tracing
