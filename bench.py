@@ -29,6 +29,7 @@ UNIT = "interactions/s"
 WORKLOAD = "c2_4f_telescope"
 BYTES_PER_INTERACTION = 208  # read + write one 104-B ray record per interaction (wavefront form)
 # fp64 flops per interaction of this workload, from the ncu instruction counts of profiles/ 
+E2E_EXTRA = {}
 FLOPS_PER_INTERACTION = 1534  # executed (2*DFMA + DMUL + DADD) / interactions, profiles/r1_trace_kernel_summary.md (r1e)
 
 
@@ -335,6 +336,26 @@ def run_e2e(args, engine, dt, bundle, n, hit_cap, hit_columns, hit_dtypes, row_b
     e2e_value = inter_all * e2e_steps / e2e_s
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = hits_per_step * row_bytes + hy.numel() * 8 + hyz.numel() * 8 + A.C_COUNT * 8
+    # for information: the same call when the caller only wants the monitors' histograms back (no row columns)
+    import copy
+
+    prm2 = copy.copy(dt.prm)
+    prm2.record_hits = 0
+    res2 = A.Result()
+    res2.hist_y, res2.hist_yz, res2.counters = hy.data_ptr(), hyz.data_ptr(), hc.data_ptr()
+    engine.trace_host(dt.scene, rs, prm2, res2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        engine.trace_host(dt.scene, rs, prm2, res2)
+    torch.cuda.synchronize()
+    hist_s = time.perf_counter() - t0
+    if world > 1:
+        te = torch.tensor([hist_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        hist_s = float(te.item())
+    E2E_EXTRA["e2e_histograms_only"] = {"value": inter_all * e2e_steps / hist_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                                        "d2h_bytes_per_step": int(hy.numel() * 8 + hyz.numel() * 8 + A.C_COUNT * 8)}
     return e2e_value, h2d, d2h, e2e_steps
 
 
@@ -375,7 +396,7 @@ def finish(args, engine, flat, world, rank, n, inter_per_step, hits_per_step, la
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "optb_trace_host (C ABI, pinned host buffers)"},
-            "roofline": roofline, "roofline_fp64": roofline_fp64,
+            **E2E_EXTRA, "roofline": roofline, "roofline_fp64": roofline_fp64,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"first {args.cpu_rays} rays of the same batch ({cpu_inter} interactions in {cpu_dt:.2f} s), "
                                        f"oracle/optb_oracle.c with {threads} threads"}}
