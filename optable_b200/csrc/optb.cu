@@ -290,6 +290,9 @@ template <bool SMEM, bool SERIAL>
 __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
+  // The closest-hit search only needs a ray's geometry. Its radiometric state (intensity, wavelength, q, path
+  // length, index: 12 registers) is parked here for the duration of the search so that the hot loop has them.
+  __shared__ double s_park[6][kBlock];
   const unsigned char* base = a.blob;
   if constexpr (SMEM) {
     // Stage the whole scene blob with TMA bulk copies; completion is signalled on the mbarrier.
@@ -390,7 +393,14 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
     while (true) {
       if ((long long)ray.pop >= a.max_trace) { c_drop++; nch = 0; break; }  // queued but never popped
       double t; int node;
-      closest_hit(a, sv, ray, solo, t, node, c_tests);
+      {
+        volatile double* pk = &s_park[0][threadIdx.x];
+        pk[0 * kBlock] = ray.I; pk[1 * kBlock] = ray.wl; pk[2 * kBlock] = ray.qre;
+        pk[3 * kBlock] = ray.qim; pk[4 * kBlock] = ray.pl; pk[5 * kBlock] = ray.n;
+        closest_hit(a, sv, ray, solo, t, node, c_tests);
+        ray.I = pk[0 * kBlock]; ray.wl = pk[1 * kBlock]; ray.qre = pk[2 * kBlock];
+        ray.qim = pk[3 * kBlock]; ray.pl = pk[4 * kBlock]; ray.n = pk[5 * kBlock];
+      }
       c_pops++;
       // the pop's dead segment: the ray itself when nothing was hit (optical_table.py:132-134), else the
       // truncated copy with length = t, alive = False (optical_component.py:364)
