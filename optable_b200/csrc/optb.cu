@@ -11,6 +11,7 @@
 //   mark_kernel       first/last wavefront index of every root (rank of a ray inside its root's generation).
 // Segments and monitor rows are appended with warp-aggregated atomics and carry their (root, pop) key.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <stddef.h>
 #include <stdio.h>
 #include <string.h>
@@ -36,6 +37,7 @@ constexpr int kRayF64 = 13;
 struct RayBuf {
   double* f[kRayF64];  // ox oy oz dx dy dz I wl qre qim pl n len
   uint32_t* flags; uint32_t* root; uint32_t* pop; int32_t* family;
+  uint32_t* key;  // coherence key of a child: (leaf it left) * 2 + child index
 };
 
 struct Header {  // first bytes of the workspace
@@ -52,6 +54,7 @@ struct TraceArgs {
   optb_rays in0; RayBuf w; int gen0;
   long long n_in; const unsigned int* n_in_dev;  // n_in_dev overrides when non-null
   const uint32_t* gen_first; const uint32_t* gen_last;
+  const uint32_t* perm;  // processing order of the wavefront (sorted by coherence key), or null
   // split output
   RayBuf c; uint8_t* nchild;
   // params
@@ -127,12 +130,14 @@ OPTB_DEV void load_ray(const TraceArgs& a, long long i, Ray& r, bool& solo, uint
   }
 }
 
-OPTB_DEV void store_child(const RayBuf& c, long long j, const Ray& parent, const Children& ch, int k, uint32_t pop_base) {
+OPTB_DEV void store_child(const RayBuf& c, long long j, const Ray& parent, const Children& ch, int k, uint32_t pop_base,
+                           int leaf) {
   c.f[0][j] = ch.ox; c.f[1][j] = ch.oy; c.f[2][j] = ch.oz;
   c.f[3][j] = ch.dx[k]; c.f[4][j] = ch.dy[k]; c.f[5][j] = ch.dz[k];
   c.f[6][j] = ch.I[k]; c.f[7][j] = parent.wl; c.f[8][j] = ch.qre[k]; c.f[9][j] = ch.qim[k];
   c.f[10][j] = ch.pl; c.f[11][j] = ch.nmed[k]; c.f[12][j] = parent.len;
   c.flags[j] = parent.flags; c.root[j] = parent.root; c.pop[j] = pop_base; c.family[j] = parent.family;
+  c.key[j] = ((uint32_t)leaf << 1) | (uint32_t)k;
 }
 
 OPTB_DEV void ring_put(const RayBuf& w, long long j, const Ray& r) {
@@ -335,6 +340,9 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
     long long i = (long long)chunk * 32 + lane;
     if ((long long)chunk * 32 >= n_in) break;
     if (i >= n_in) continue;
+    // Wavefront entries are stored in reference (BFS) order, which the pop numbering needs, but processed in the
+    // order of their coherence key: rays that left the same surface the same way sit in the same warp.
+    if (!SERIAL && a.perm) i = a.perm[i];
 
     if constexpr (SERIAL) {
       // Work item = one Ray._id family. Its initial rays are traced one after another in input order, each
@@ -388,6 +396,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
     const uint32_t pop_base_next = a.gen0 ? 0u : (a.w.pop[i] + gcount);
     int nch = 0;
     int chained = 0;
+    int hit_leaf = 0;
     Children ch;
     ch.n = 0;
     while (true) {
@@ -411,6 +420,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
                    hit ? ni[OPTB_NI_LEAF] : -1, s_hist, c_hits);
       if (!hit) { nch = 0; break; }
       c_inter++;
+      hit_leaf = ni[OPTB_NI_LEAF];
       double ox, oy, oz, dx, dy, dz;
       to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
       interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch);
@@ -428,7 +438,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
     if (a.nchild) {
       a.nchild[i] = (uint8_t)nch;
       uint32_t pb = solo ? ray.pop + 1u : pop_base_next;
-      for (int k = 0; k < nch; k++) store_child(a.c, 2 * i + k, ray, ch, k, pb);
+      for (int k = 0; k < nch; k++) store_child(a.c, 2 * i + k, ray, ch, k, pb, hit_leaf);
     }
   }
 
@@ -543,6 +553,7 @@ __global__ void __launch_bounds__(kScanBlock) scatter_kernel(const uint8_t* __re
 #pragma unroll
       for (int f = 0; f < kRayF64; f++) w.f[f][dst] = c.f[f][src];
       w.flags[dst] = c.flags[src]; w.root[dst] = c.root[src]; w.pop[dst] = c.pop[src]; w.family[dst] = c.family[src];
+      w.key[dst] = c.key[src];
     }
     __syncthreads();
     if (threadIdx.x == 0) s_carry += total;
@@ -570,6 +581,18 @@ __global__ void fam_scatter_kernel(const int32_t* __restrict__ family, long long
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int f = family ? family[i] : (int32_t)i;
     roots[off[f] + atomicAdd(&cursor[f], 1u)] = (uint32_t)i;
+  }
+}
+
+// Sort input of one generation: identity permutation + the coherence key, with "this root has a single live ray"
+// (it will chain many pops in registers) as the top bit so that one-pop rays and chaining rays do not share warps.
+__global__ void sort_prep_kernel(uint32_t* __restrict__ idx, uint32_t* __restrict__ key, const uint32_t* __restrict__ root,
+                                 long long n, int key_bits) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    idx[j] = (uint32_t)j;
+    const uint32_t r = root[j];
+    const bool solo = (j == 0 || root[j - 1] != r) && (j == n - 1 || root[j + 1] != r);
+    key[j] = (key[j] & ((1u << key_bits) - 1u)) | ((solo ? 1u : 0u) << key_bits);
   }
 }
 
@@ -738,10 +761,10 @@ extern "C" int optb_scene_destroy(optb_ctx* ctx, optb_scene* s) {
 
 namespace {
 struct WsLayout {
-  size_t hdr, w, c, nchild, gen_first, gen_last, sums, total;
+  size_t hdr, w, c, nchild, gen_first, gen_last, sums, iota, perm, key_sorted, cub, cub_bytes, total;
   long long cap;  // wavefront capacity (rays)
 };
-size_t raybuf_bytes(long long cap) { return align_up((size_t)cap * 8, 256) * kRayF64 + align_up((size_t)cap * 4, 256) * 4; }
+size_t raybuf_bytes(long long cap) { return align_up((size_t)cap * 8, 256) * kRayF64 + align_up((size_t)cap * 4, 256) * 5; }
 WsLayout ws_layout(long long n_rays, long long max_live, bool split) {
   WsLayout L{};
   size_t o = 0;
@@ -754,6 +777,13 @@ WsLayout ws_layout(long long n_rays, long long max_live, bool split) {
     L.gen_first = o; o += align_up((size_t)n_rays * 4, 256);
     L.gen_last = o; o += align_up((size_t)n_rays * 4, 256);
     L.sums = o; o += align_up(((size_t)L.cap / kTile + 2) * 4, 256);
+    L.iota = o; o += align_up((size_t)L.cap * 4, 256);
+    L.perm = o; o += align_up((size_t)L.cap * 4, 256);
+    L.key_sorted = o; o += align_up((size_t)L.cap * 4, 256);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)std::min<long long>(L.cap, 0x7fffffffll), 0, 32);
+    L.cub = o; L.cub_bytes = align_up(tb + 256, 256); o += L.cub_bytes;
   }
   L.total = o;
   return L;
@@ -765,7 +795,8 @@ RayBuf make_raybuf(unsigned char* base, long long cap) {
   b.flags = (uint32_t*)(base + o); o += align_up((size_t)cap * 4, 256);
   b.root = (uint32_t*)(base + o); o += align_up((size_t)cap * 4, 256);
   b.pop = (uint32_t*)(base + o); o += align_up((size_t)cap * 4, 256);
-  b.family = (int32_t*)(base + o);
+  b.family = (int32_t*)(base + o); o += align_up((size_t)cap * 4, 256);
+  b.key = (uint32_t*)(base + o);
   return b;
 }
 bool needs_wavefront(const optb_scene* s, const optb_params* p) { return s->max_children > 1 || p->chain_len > 0; }
@@ -915,7 +946,21 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     launches += 4; gens = 1;
     n_in = 0;
   }
+  int key_bits = 1;
+  while ((1ll << key_bits) < 2ll * std::max(scene->n_leaves, 1)) key_bits++;
   while (n_in > 0) {
+    if (split && !a.gen0 && n_in >= 2048 && n_in < 0x7fffffffll) {
+      uint32_t* iota = (uint32_t*)(ws + L.iota);
+      uint32_t* perm = (uint32_t*)(ws + L.perm);
+      sort_prep_kernel<<<std::min(full_grid * 4, (int)((n_in + 255) / 256)), 256, 0, st>>>(iota, a.w.key, a.w.root, n_in, key_bits);
+      size_t tb = L.cub_bytes;
+      CK(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, (const uint32_t*)a.w.key, (uint32_t*)(ws + L.key_sorted),
+                                         (const uint32_t*)iota, perm, (int)n_in, 0, key_bits + 1, st), "radix sort");
+      a.perm = perm;
+      launches += 4;
+    } else {
+      a.perm = nullptr;
+    }
     long long want = (n_in + kBlock - 1) / kBlock;
     int grid = (int)std::min<long long>(full_grid, want);
     a.n_in = n_in;
