@@ -91,7 +91,7 @@ def alloc_result(n_seg, n_hit, n_monitors, n_capslots, n_families, cap_counts=No
 
 
 def trace(flat: FlatScene, ray_arrs, max_trace_num=2000, unit=1e-2, record_segments=True, record_hits=True,
-          record_hist=False, n_families=None, cap_counts=None, nthreads=1):
+          record_hist=False, n_families=None, cap_counts=None, nthreads=1, seg_capacity=None, hit_capacity=None):
     """Run the CPU restatement. Returns a dict of numpy arrays trimmed to the produced rows, in
     reference order: segments (root, pop); hits (root, monitor, pop)."""
     L = lib()
@@ -103,7 +103,10 @@ def trace(flat: FlatScene, ray_arrs, max_trace_num=2000, unit=1e-2, record_segme
     rs = rays_struct(ray_arrs)
     prm = make_params(max_trace_num, unit, record_segments, record_hits, record_hist, 0, n_families)
     n_seg = n_hit = 0
-    if record_segments or record_hits:
+    known = (not record_segments or seg_capacity is not None) and (not record_hits or hit_capacity is not None)
+    if known:  # capacities given by the caller: no counting pass (used when this run is being timed)
+        n_seg, n_hit = int(seg_capacity or 0) if record_segments else 0, int(hit_capacity or 0) if record_hits else 0
+    elif record_segments or record_hits:
         scratch = None
         if flat.n_capslots:
             scratch = np.array(cap_counts if cap_counts is not None
@@ -118,6 +121,10 @@ def trace(flat: FlatScene, ray_arrs, max_trace_num=2000, unit=1e-2, record_segme
     if rc != 0:
         raise RuntimeError(f"optb_oracle_trace failed: {rc}")
     arrs["counters"][A.C_SEGMENTS] = n_seg if record_segments else -1
+    if known and record_hits:  # trim to the rows produced
+        rows = int(arrs["counters"][A.C_HITS])
+        for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64:
+            arrs[k] = arrs[k][:rows]
     return arrs
 
 
