@@ -686,6 +686,36 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   if (!ctx || !d || !out) return -1;
   if (d->abi_version != OPTB_ABI_VERSION) return fail(ctx, -4, "scene ABI version mismatch");
   if (d->n_nodes < 0 || d->n_materials < 1) return fail(ctx, -5, "bad scene counts");
+  // The kernels index the tables without bounds checks: reject anything that could walk out of them.
+  for (int i = 0; i < d->n_nodes; i++) {
+    const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
+    const int g = ni[OPTB_NI_GEOM];
+    if (ni[OPTB_NI_SKIP] <= i || ni[OPTB_NI_SKIP] > d->n_nodes) return fail(ctx, -5, "scene: node skip pointer out of range");
+    if (g < OPTB_G_GROUP || g > OPTB_G_CSG) return fail(ctx, -5, "scene: unknown geometry kind");
+    if (g == OPTB_G_GROUP) continue;
+    if (ni[OPTB_NI_SKIP] != i + 1) return fail(ctx, -5, "scene: a leaf must skip to the next node");
+    if (ni[OPTB_NI_INTER] < OPTB_I_MIRROR || ni[OPTB_NI_INTER] > OPTB_I_ABSORB) return fail(ctx, -5, "scene: unknown interaction kind");
+    if (ni[OPTB_NI_MAT1] < 0 || ni[OPTB_NI_MAT1] >= d->n_materials || ni[OPTB_NI_MAT2] < 0 || ni[OPTB_NI_MAT2] >= d->n_materials)
+      return fail(ctx, -5, "scene: material index out of range");
+    if (ni[OPTB_NI_CAPSLOT] >= d->n_capslots) return fail(ctx, -5, "scene: cap slot out of range");
+    if (ni[OPTB_NI_LEAF] < 0 || ni[OPTB_NI_LEAF] >= d->n_leaves) return fail(ctx, -5, "scene: leaf index out of range");
+    auto poly_ok = [&](long long off) {
+      if (off < 0 || off + OPTB_POLY_HEADER > d->n_aux) return false;
+      const double nv = d->aux[off];
+      return nv >= 3 && nv <= 1e6 && off + OPTB_POLY_HEADER + 2 * (long long)nv <= d->n_aux;
+    };
+    const double* p = d->node_f + (size_t)i * OPTB_NF_STRIDE + OPTB_NF_P;
+    if ((g == OPTB_G_POLY2D || g == OPTB_G_POLY3D) && !poly_ok(ni[OPTB_NI_AUX])) return fail(ctx, -5, "scene: polygon record out of range");
+    if (g == OPTB_G_ASPHERE && ni[OPTB_NI_AUX] != OPTB_ASPH_PARAMETRIC && ni[OPTB_NI_AUX] != OPTB_ASPH_EXACT_SPH)
+      return fail(ctx, -5, "scene: unknown asphere form");
+    if (g == OPTB_G_CSG) {
+      for (int q = 0; q < 2; q++) {
+        const int k = (int)p[1 + 3 * q];
+        if (k != OPTB_G_CIRCLE && k != OPTB_G_RECT && k != OPTB_G_POLY2D) return fail(ctx, -5, "scene: bad CSG operand");
+        if (k == OPTB_G_POLY2D && !poly_ok((long long)p[2 + 3 * q])) return fail(ctx, -5, "scene: CSG polygon out of range");
+      }
+    }
+  }
   cudaSetDevice(ctx->device);
   optb_scene* s = new (std::nothrow) optb_scene();
   if (!s) return -3;
@@ -1079,12 +1109,12 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     CK(cudaMemsetAsync(d_hy, 0, hy, ctx->s_run), "memset hist");
     CK(cudaMemsetAsync(d_hyz, 0, hyz, ctx->s_run), "memset hist");
   }
-  std::vector<cudaEvent_t> ev_h2d(nch), ev_run(nch), ev_d2h(nch);
-  for (int c = 0; c < nch; c++) {
-    cudaEventCreateWithFlags(&ev_h2d[c], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_run[c], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_d2h[c], cudaEventDisableTiming);
-  }
+  struct Events {  // destroyed on every exit path
+    std::vector<cudaEvent_t> v;
+    explicit Events(int n) : v(n) { for (auto& e : v) cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+    ~Events() { for (auto& e : v) cudaEventDestroy(e); }
+    cudaEvent_t& operator[](int i) { return v[i]; }
+  } ev_h2d(nch), ev_run(nch), ev_d2h(nch);
   unsigned long long tot[OPTB_C_COUNT] = {0};
   int64_t seg_off = 0, hit_off = 0;
   bool chunk_overflow = false;
@@ -1140,7 +1170,6 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
   }
   cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_run);
   cudaError_t e = cudaStreamSynchronize(ctx->s_d2h);
-  for (int c = 0; c < nch; c++) { cudaEventDestroy(ev_h2d[c]); cudaEventDestroy(ev_run[c]); cudaEventDestroy(ev_d2h[c]); }
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, -10, "pipelined trace", e);
   if (chunk_overflow) return 1;

@@ -112,3 +112,19 @@ def test_abcd_matrix_and_4f_calibration_callers():
     assert Ms.shape == (7, 2, 2) and abs(Ms[3, 0, 0] + 1) < 0.2   # a 4f relay images with magnification about -1
     F = ob.OpticalTable.calibrate_symmetric_4f(lens, rays[2:5], F10=F1, F20=F2, criterion="min_stdtY", optimize=True)
     assert len(F) == 2 and all(np.isfinite(F)) and abs(F[0] - F1) < 5
+
+
+def test_scene_upload_rejects_malformed_tables():
+    """The kernels index the tables without bounds checks, so optb_scene_upload validates them."""
+    from optable_b200 import _abi as A
+    from optable_b200.backend import BackendError, Engine
+
+    engine = Engine.get(0)
+    flat, _, _, _ = golden_io.load("dove_prism")
+    for col, val in ((A.NI_SKIP, 0), (A.NI_GEOM, 99), (A.NI_MAT1, 1000), (A.NI_AUX, 10 ** 6)):
+        bad, _, _, _ = golden_io.load("dove_prism")
+        leaf = int(np.nonzero(bad.node_i[:, A.NI_GEOM] == A.G_POLY3D)[0][0])
+        bad.node_i[leaf, col] = val
+        with pytest.raises(BackendError):
+            engine.upload(bad)
+    engine.upload(flat).close()
