@@ -317,6 +317,31 @@ def ripa(ns, n_rays=1, limit=300, jitter=True):
     return sc
 
 
+def extras(ns):
+    """Corner cases the example scenes do not reach: a union aperture (Plane.union, surfaces.py:100-117), a
+    non-orthonormal transform_matrix (sheared/scaled by hand: the to-local normalisation really matters), a diverging
+    thin lens, a full-circle cylinder mirror hit from inside, a polygonal mirror, rays without wavelength and with a
+    length limit that ends between two surfaces."""
+    m_union = ns.SquareMirror([4, 0, 0], width=1, height=1, reflectivity=0.7, transmission=0.3)
+    m_union.surface = ns.Circle(0.6).union(ns.Rectangle(2.4, 0.3))
+    skew = ns.SquareRefractive([7, 0.2, 0], width=3, height=3, n1=1.0, n2=1.4, reflectivity=0.1).RotZ(0.2)
+    skew.transform_matrix = skew.transform_matrix @ np.array([[1.0, 0.15, 0.0], [0.0, 1.3, 0.1], [0.0, 0.0, 0.8]])
+    lens = ns.Lens([10, 0, 0], focal_length=-3.0, radius=1.5, transmission=0.9)
+    cyl = ns.CylMirror([16, 0, 0], radius=2.5, height=4.0)
+    tri = ns.BaseMirror([-4, 0, 0], reflectivity=1.0)
+    tri.surface = ns.Polygon([[-1.0, -1.2], [1.4, -0.8], [0.2, 1.5]])
+    tri.RotZ(np.pi).RotY(0.15)
+    rng = np.random.default_rng(SEED + 7)
+    rays = []
+    for k in range(14):
+        y, z = rng.uniform(-0.5, 0.5, 2)
+        kw = dict(wavelength=633e-7, w0=40e-4) if k % 3 else {}
+        rays.append(ns.Ray([0, y, z], [1, 0.05 * rng.standard_normal(), 0.05 * rng.standard_normal()], **kw))
+    rays.append(ns.Ray([0, 0.1, 0.1], [1, 0, 0], length=5.5, wavelength=500e-7, w0=20e-4))
+    rays.append(ns.Ray([0, -0.1, 0.2], [-1, 0.02, 0.01]))
+    return Scene([m_union, skew, lens, cyl, tri], rays, [ns.Monitor([12, 0, 0], 8, 8).RotY(0.1)], limit={"max_trace_num": 40})
+
+
 def caps_binding(ns):
     """Interact caps that really bind: a TriangularPrism whose faces 2/3 stop interacting after 3 hits
     per ray id, partial reflections everywhere (splitting), and each ray multiplexed into 6 wavelengths that share
@@ -347,6 +372,7 @@ REGISTRY = {
     "misc_components": misc_components,
     "mma_small": mma_small,
     "caps_binding": caps_binding,
+    "extras": extras,
     "ripa": lambda ns: ripa(ns, n_rays=3, limit=150),
 }
 
