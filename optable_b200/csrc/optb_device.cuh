@@ -231,6 +231,24 @@ struct AsphF {
     }
     return fma(R, sqrt(fma(k1, r2, 1.0)) - 1.0, Px);
   }
+  // g and dg/dt at t (for the Newton refinement of a bracketed root)
+  OPTB_DEV void eval2(double t, double& g, double& dg) const {
+    double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+    double r2 = fma(Py, Py, Pz * Pz);
+    double r2p = 2.0 * fma(Py, dy, Pz * dz);
+    if (form == OPTB_ASPH_PARAMETRIC) {
+      double s = sqrt(fma(-k1, r2, 1.0));
+      double lin = fma(r2 * r2, fma(r2, fma(r2, a8, a6), a4), Px);
+      double linp = fma(r2 * fma(r2, fma(r2, 4.0 * a8, 3.0 * a6), 2.0 * a4), r2p, dx);
+      double sp = -0.5 * k1 * r2p / s;
+      g = sgn * fma(lin * R, 1.0 + s, r2);
+      dg = sgn * (fma(linp * R, 1.0 + s, lin * R * sp) + r2p);
+    } else {
+      double h = sqrt(fma(k1, r2, 1.0));
+      g = fma(R, h - 1.0, Px);
+      dg = fma(0.5 * R * k1 / h, r2p, dx);
+    }
+  }
   // Same sign as operator()(t) (NaN where the reference's f is NaN), without the square root:
   // g = sgn * (A s + B) with s = sqrt(s2) >= 0; when A and B disagree in sign the comparison is done on squares.
   OPTB_DEV double sign(double t) const {
@@ -253,43 +271,26 @@ struct AsphF {
   }
 };
 
+// Root of a smooth f inside a bracket with f(lo) f(hi) < 0: safeguarded Newton from the secant point (a step that
+// would leave the bracket is replaced by a bisection). The reference gets this root from scipy's brentq, whose
+// answer is only defined to xtol = 2e-12; converging to the last bit instead stays well inside that.
 template <class F>
-OPTB_DEV double brentq(const F& f, double xa, double xb, double fa, double fb) {
-  const double xtol = 2e-12, rtol = 8.881784197001252e-16;
-  double xpre = xa, xcur = xb, xblk = 0., fpre = fa, fcur = fb, fblk = 0., spre = 0., scur = 0.;
-  if (fpre == 0) return xpre;
-  if (fcur == 0) return xcur;
-  for (int i = 0; i < 100; i++) {
-    if (fpre != 0 && fcur != 0 && (signbit(fpre) != signbit(fcur))) {
-      xblk = xpre; fblk = fpre; spre = scur = xcur - xpre;
-    }
-    if (fabs(fblk) < fabs(fcur)) {
-      xpre = xcur; xcur = xblk; xblk = xpre;
-      fpre = fcur; fcur = fblk; fblk = fpre;
-    }
-    double delta = (xtol + rtol * fabs(xcur)) / 2;
-    double sbis = (xblk - xcur) / 2;
-    if (fcur == 0 || fabs(sbis) < delta) return xcur;
-    if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
-      double stry;
-      if (xpre == xblk) {
-        stry = -fcur * (xcur - xpre) / (fcur - fpre);
-      } else {
-        double dpre = (fpre - fcur) / (xpre - xcur);
-        double dblk = (fblk - fcur) / (xblk - xcur);
-        stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
-      }
-      if (2 * fabs(stry) < fmin(fabs(spre), 3 * fabs(sbis) - delta)) { spre = scur; scur = stry; }
-      else { spre = sbis; scur = sbis; }
-    } else {
-      spre = sbis; scur = sbis;
-    }
-    xpre = xcur; fpre = fcur;
-    if (fabs(scur) > delta) xcur += scur;
-    else xcur += (sbis > 0 ? delta : -delta);
-    fcur = f(xcur);
+OPTB_DEV double newton_bracketed(const F& f, double lo, double hi, double glo, double ghi) {
+  if (glo == 0.0) return lo;
+  if (ghi == 0.0) return hi;
+  double x = lo - glo * (hi - lo) / (ghi - glo);
+  const bool lo_pos = glo > 0.0;
+  for (int it = 0; it < 12; it++) {
+    double g, dg;
+    f.eval2(x, g, dg);
+    if (g == 0.0) break;
+    if ((g > 0.0) == lo_pos) lo = x; else hi = x;
+    double xn = x - g / dg;
+    if (fabs(xn - x) <= 2e-15 * fmax(fabs(x), 1.0)) { x = xn; break; }  // converged to rounding level
+    if (!(xn > fmin(lo, hi) && xn < fmax(lo, hi))) xn = 0.5 * (lo + hi);
+    x = xn;
   }
-  return xcur;
+  return x;
 }
 
 // np.linspace(a, b, 10)[i]
@@ -385,7 +386,7 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
         }
       }
       if (solve) {
-        double r = brentq(f, lo, tb, f(lo), f(tb));
+        double r = newton_bracketed(f, lo, tb, f(lo), f(tb));
         if (r >= 1e-9 && r <= len) {
           double Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
           if (sqrt(fma(Py, Py, Pz * Pz)) <= p[0] + 1e-12) {   // ASphere.within_boundary
