@@ -298,6 +298,11 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
   // The closest-hit search only needs a ray's geometry. Its radiometric state (intensity, wavelength, q, path
   // length, index: 12 registers) is parked here for the duration of the search so that the hot loop has them.
   __shared__ double s_park[6][kBlock];
+  __shared__ double s_icn[3][kBlock];   // index memo: wavelength, n of slot 0, n of slot 1
+  __shared__ int s_icm[2][kBlock];      // material index of slot 0 / slot 1
+  s_icn[0][threadIdx.x] = -1.0; s_icm[0][threadIdx.x] = -1; s_icm[1][threadIdx.x] = -1;
+  const IndexCache ic{&s_icn[0][threadIdx.x], &s_icn[1][threadIdx.x], &s_icn[2][threadIdx.x], &s_icm[0][threadIdx.x],
+                      &s_icm[1][threadIdx.x]};
   const unsigned char* base = a.blob;
   if constexpr (SMEM) {
     // Stage the whole scene blob with TMA bulk copies; completion is signalled on the mbarrier.
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
           double ox, oy, oz, dx, dy, dz;
           to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
           Children ch;
-          interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch);
+          interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
           for (int k = 0; k < ch.n; k++) {
             if (tail - head >= a.qcap) { atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_WORK_OVERFLOW); break; }
             Ray c = ray;
@@ -423,7 +428,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
       hit_leaf = ni[OPTB_NI_LEAF];
       double ox, oy, oz, dx, dy, dz;
       to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
-      interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch);
+      interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
       nch = ch.n;
       if (nch == 1 && solo && (a.chain_len == 0 || chained + 1 < a.chain_len)) {
         // the root's alive set is this one ray: BFS order is trivially kept, continue in registers

@@ -493,6 +493,24 @@ OPTB_DEV double material_n(const SceneView& sv, int m, double wl_m) {
   return sqrt(n2);
 }
 
+// Per-thread memo of Sellmeier evaluations: a ray keeps its wavelength for life and meets the same one or two glasses
+// again and again (every face of a lens), so n(material, wavelength) is looked up in two slots kept in shared memory
+// before paying three divisions and a square root. Slots are keyed by (wavelength, material index).
+struct IndexCache {
+  volatile double* wl; volatile double* n0; volatile double* n1; volatile int* m0; volatile int* m1;
+};
+OPTB_DEV double material_n_cached(const SceneView& sv, const IndexCache& c, int m, double wl_m) {
+  if (sv.matk[m] == OPTB_MAT_CONST) return sv.matf[m * OPTB_MF_STRIDE];
+  const bool same_wl = (*c.wl == wl_m);
+  if (same_wl && *c.m0 == m) return *c.n0;
+  if (same_wl && *c.m1 == m) return *c.n1;
+  const double n = material_n(sv, m, wl_m);
+  if (!same_wl) { *c.wl = wl_m; *c.m0 = m; *c.n0 = n; *c.m1 = -1; }
+  else if (*c.m1 < 0 || (m & 1)) { *c.m1 = m; *c.n1 = n; }
+  else { *c.m0 = m; *c.n0 = n; }
+  return n;
+}
+
 // numpy complex128 division (Smith)
 OPTB_DEV void cdiv(double a, double b, double c, double d, double& re, double& im) {
   if (fabs(c) >= fabs(d)) {
@@ -531,7 +549,7 @@ OPTB_DEV void dir_to_lab(const double* __restrict__ T, bool ortho, double lx, do
 // interact_local bodies for the winning leaf. (ox..dz) is the ray in the leaf's local frame, t the hit parameter.
 OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
                        const Ray& ray, double unit, double ox, double oy, double oz, double dx, double dy, double dz,
-                       double t, Children& ch) {
+                       double t, Children& ch, const IndexCache& ic) {
   const double* T = nf + OPTB_NF_T;
   const double* c = nf + OPTB_NF_ORIGIN;
   const bool ortho = ni[OPTB_NI_ORTHO] != 0;
@@ -578,8 +596,8 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
   }
   // BaseRefraciveSurface :617-717, children [transmitted | TIR, reflected]
   double wl_m = ray.wl * unit;
-  double n1 = material_n(sv, ni[OPTB_NI_MAT1], wl_m);
-  double n2 = material_n(sv, ni[OPTB_NI_MAT2], wl_m);
+  double n1 = material_n_cached(sv, ic, ni[OPTB_NI_MAT1], wl_m);
+  double n2 = material_n_cached(sv, ic, ni[OPTB_NI_MAT2], wl_m);
   double ROC = INFINITY;
   int rk = ni[OPTB_NI_ROCKIND];
   if (rk == OPTB_ROC_CONST) ROC = nf[OPTB_NF_ROC];
