@@ -184,7 +184,7 @@ OPTB_DEV bool poly_within(const double* __restrict__ rec, double Px, double Py, 
 }
 
 OPTB_DEV bool planar_within(const SceneView& sv, int kind, double p0, double p1, double Px, double Py, double Pz) {
-  if (kind == OPTB_G_CIRCLE) return sqrt(dot3(Px, Py, Pz, Px, Py, Pz)) <= p0;  // surfaces.py:144-145 (3-D norm)
+  if (kind == OPTB_G_CIRCLE) return dot3(Px, Py, Pz, Px, Py, Pz) <= p0 * p0 && p0 >= 0.0;  // |P| <= r (3-D norm, surfaces.py:144-145), on squares
   if (kind == OPTB_G_RECT) return fabs(Py) <= p0 && fabs(Pz) <= p1;            // surfaces.py:170-171
   if (kind == OPTB_G_POLY2D) return poly_within(sv.aux + (long long)p0, Px, Py, Pz);
   return false;
@@ -389,7 +389,8 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
         double r = newton_bracketed(f, lo, tb, f(lo), f(tb));
         if (r >= 1e-9 && r <= len) {
           double Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
-          if (sqrt(fma(Py, Py, Pz * Pz)) <= p[0] + 1e-12) {   // ASphere.within_boundary
+          const double rmax = p[0] + 1e-12;
+          if (fma(Py, Py, Pz * Pz) <= rmax * rmax) {   // ASphere.within_boundary (r <= radius + 1e-12, on squares)
             if (asc) return r;   // sub-intervals ascend: the first admissible root is the smallest
             if (best < 0 || r < best) best = r;
           }
@@ -610,12 +611,13 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
   double cos_i = fmin(fmax(dn, -1.0), 1.0);
   double sin_i = sqrt(1.0 - cos_i * cos_i);
   double sin_t = (nin * sin_i) / nout;
+  const double ratio = nin / nout;  // D of the refraction ABCD and the tangential scale of Snell's law
   double qtr = 0, qti = 0, qrr = 0, qri = 0;
   if (hasq) {  // ABCD of the refraction / of the reflection (:648-666); each only when a child will carry it
     double qr = ray.qre + t, qi = ray.qim;
     if (sin_t < 1 && trans > 0) {
-      double Cc = (nin - nout) / (ROC * nout), D = nin / nout;
-      cdiv(qr, qi, fma(Cc, qr, D), Cc * qi, qtr, qti);
+      double Cc = (nin - nout) / (ROC * nout);
+      cdiv(qr, qi, fma(Cc, qr, ratio), Cc * qi, qtr, qti);
     }
     if (!(sin_t < 1) || refl > 0) {
       double C2 = 2.0 / ROC;
@@ -628,7 +630,7 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
   if (sin_t < 1) {
     if (trans > 0) {
       double cos_t = sqrt(1.0 - sin_t * sin_t);
-      double kk = nin / nout, cs = cos_t * sgn;
+      double kk = ratio, cs = cos_t * sgn;
       dir_to_lab(T, ortho, fma(kk, rtx, cs * nx), fma(kk, rty, cs * ny), fma(kk, rtz, cs * nz), ch.dx[k], ch.dy[k], ch.dz[k]);
       ch.I[k] = ray.I * trans; ch.qre[k] = qtr; ch.qim[k] = qti; ch.nmed[k] = nout; k++;
     }
