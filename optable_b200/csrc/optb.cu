@@ -67,6 +67,7 @@ struct TraceArgs {
   // reference's sequential order; w is then a per-family FIFO ring of qcap entries
   const uint32_t* fam_off; uint32_t* fam_roots; uint32_t qcap;
   uint32_t root_base;  // global index of ray 0 of this launch (chunked host traces)
+  int has_boxes;       // some node carries a lab-box test
 };
 
 OPTB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -249,6 +250,7 @@ struct HitSearch {
   }
 };
 
+template <bool BOXES>
 OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
                           double& best_t, int& best_node, unsigned int& tests) {
   best_t = INFINITY; best_node = -1;
@@ -259,7 +261,8 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   int n_parked = 0, n_done = 0;
   int i = 0;
   const int n = sv.n_nodes;
-  const BoxRay br(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz);
+  // BOXES = false: a scene of top-level leaves only has no box test at all (and pays no reciprocals for one)
+  const BoxRay br(ray.ox, ray.oy, ray.oz, BOXES ? ray.dx : 1.0, BOXES ? ray.dy : 1.0, BOXES ? ray.dz : 1.0);
   // One loop, one test_leaf call site (the leaf test is ~2/3 of the kernel's code; inlining it twice thrashes the
   // instruction cache): first the pre-order walk, then the parked aspheres.
   while (true) {
@@ -267,7 +270,7 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
     while (i < n) {
       const double* tv = sv.trav + i * 8;
       const int2 gs = *reinterpret_cast<const int2*>(tv + 6);  // {geometry kind, skip}
-      if (*reinterpret_cast<const int*>(tv + 7) && !slab_hit(br, tv)) { i = gs.y; continue; }
+      if (BOXES && *reinterpret_cast<const int*>(tv + 7) && !slab_hit(br, tv)) { i = gs.y; continue; }
       const int g = gs.x;
       const int cur = i++;
       if (g == OPTB_G_GROUP) continue;
@@ -291,7 +294,7 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   best_t = hs.best_t; best_node = hs.best_node;
 }
 
-template <bool SMEM, bool SERIAL>
+template <bool SMEM, bool SERIAL, bool BOXES>
 __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
           ring_get(a.w, ring + head % a.qcap, ray); head++;
           ray.root = root; ray.family = (int32_t)i; ray.pop = pops++;
           double t; int node;
-          closest_hit(a, sv, ray, true, t, node, c_tests);
+          closest_hit<BOXES>(a, sv, ray, true, t, node, c_tests);
           c_pops++;
           const bool hit = node >= 0;
           const int32_t* ni = sv.ni + (hit ? node : 0) * OPTB_NI_STRIDE;
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
         volatile double* pk = &s_park[0][threadIdx.x];
         pk[0 * kBlock] = ray.I; pk[1 * kBlock] = ray.wl; pk[2 * kBlock] = ray.qre;
         pk[3 * kBlock] = ray.qim; pk[4 * kBlock] = ray.pl; pk[5 * kBlock] = ray.n;
-        closest_hit(a, sv, ray, solo, t, node, c_tests);
+        closest_hit<BOXES>(a, sv, ray, solo, t, node, c_tests);
         ray.I = pk[0 * kBlock]; ray.wl = pk[1 * kBlock]; ray.qre = pk[2 * kBlock];
         ray.qim = pk[3 * kBlock]; ray.pl = pk[4 * kBlock]; ray.n = pk[5 * kBlock];
       }
@@ -638,7 +641,7 @@ struct optb_ctx {
 struct optb_scene {
   unsigned char* d_blob; uint32_t blob_bytes; SceneOff off;
   int n_nodes, n_leaves, n_mats, n_mons, n_caps; long long n_aux;
-  int max_children;
+  int max_children; int has_boxes;
   bool in_smem; bool hist_smem; uint32_t smem_bytes;
 };
 
@@ -762,6 +765,7 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   for (int i = 0; i < d->n_nodes; i++) {
     const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
     const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
+    if (ni[OPTB_NI_AABB]) s->has_boxes = 1;
     int k = 0;
     switch (ni[OPTB_NI_INTER]) {
       case OPTB_I_MIRROR: k = (nf[OPTB_NF_REFL] > 0) + (nf[OPTB_NF_TRANS] > 0); break;
@@ -942,6 +946,7 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   a.counters = (unsigned long long*)out->counters;
   a.hdr = hdr;
   a.root_base = root_base;
+  a.has_boxes = scene->has_boxes;
   if (split) {
     a.w = make_raybuf(ws + L.w, cap);
     a.c = make_raybuf(ws + L.c, 2 * cap);
@@ -950,8 +955,11 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     a.gen_last = (uint32_t*)(ws + L.gen_last);
   }
   uint32_t smem = scene->in_smem ? scene->smem_bytes : (a.hist_smem ? scene->smem_bytes : 0);
-  auto kern = serial ? (scene->in_smem ? trace_kernel<true, true> : trace_kernel<false, true>)
-                     : (scene->in_smem ? trace_kernel<true, false> : trace_kernel<false, false>);
+  using Kern = void (*)(const TraceArgs);
+  static const Kern table[2][2][2] = {
+      {{trace_kernel<false, false, false>, trace_kernel<false, false, true>}, {trace_kernel<false, true, false>, trace_kernel<false, true, true>}},
+      {{trace_kernel<true, false, false>, trace_kernel<true, false, true>}, {trace_kernel<true, true, false>, trace_kernel<true, true, true>}}};
+  Kern kern = table[scene->in_smem ? 1 : 0][serial ? 1 : 0][scene->has_boxes ? 1 : 0];
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
   int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem), "occupancy");
