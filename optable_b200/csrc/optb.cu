@@ -225,6 +225,7 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
 // iterative root solve each) are parked and tested last, when the closest cheap hit is known: a parked asphere
 // whose bracket starts beyond that hit is dismissed without evaluating its profile once. The (t, index) ordering
 // makes the result independent of the visiting order.
+template <bool ASPH>
 struct HitSearch {
   const TraceArgs& a; const SceneView& sv; const Ray& ray; bool solo;
   double best_t; int best_node; unsigned int& tests;
@@ -235,7 +236,7 @@ struct HitSearch {
     tests++;
     const int slot = ni[OPTB_NI_CAPSLOT];
     // a capped surface counts every geometric hit, closest or not (optical_component.py:359-362): no early exit
-    double t = intersect_leaf(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len, slot >= 0 ? INFINITY : best_t);
+    double t = intersect_leaf<ASPH>(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len, slot >= 0 ? INFINITY : best_t);
     if (!(t >= 0.0)) return;
     if (slot >= 0) {  // should_interact / increase_interact_count :136-149
       int32_t* cnt = a.out.cap_counts + (long long)slot * a.n_families + ray.family;
@@ -250,12 +251,12 @@ struct HitSearch {
   }
 };
 
-template <bool BOXES>
+template <bool BOXES, bool ASPH>
 OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
                           double& best_t, int& best_node, unsigned int& tests) {
   best_t = INFINITY; best_node = -1;
-  if (!(ray.flags & OPTB_RF_ALIVE)) return;  // optical_component.py:349-350
-  HitSearch hs{a, sv, ray, solo, INFINITY, -1, tests};
+  const bool no_work = !(ray.flags & OPTB_RF_ALIVE);  // optical_component.py:349-350: a dead ray hits nothing
+  HitSearch<ASPH> hs{a, sv, ray, solo, INFINITY, -1, tests};
   constexpr int kPark = 4;
   int parked[kPark];
   int n_parked = 0, n_done = 0;
@@ -263,38 +264,49 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   const int n = sv.n_nodes;
   // BOXES = false: a scene of top-level leaves only has no box test at all (and pays no reciprocals for one)
   const BoxRay br(ray.ox, ray.oy, ray.oz, BOXES ? ray.dx : 1.0, BOXES ? ray.dy : 1.0, BOXES ? ray.dz : 1.0);
-  // One loop, one test_leaf call site (the leaf test is ~2/3 of the kernel's code; inlining it twice thrashes the
-  // instruction cache): first the pre-order walk, then the parked aspheres.
-  while (true) {
+  // Warp-synchronous "walk, then test": in every round each lane walks boxes until it holds a leaf (or runs out of
+  // nodes and takes a parked asphere), then the lanes that called in together meet again at the vote and run the
+  // one, long leaf test side by side. Without the explicit vote the compiler is free to fold the test into the
+  // walk loop, and lanes that reach their leaves at different box counts then execute it one after another
+  // (measured: 3x on the 7,689-leaf scene). One test_leaf call site also keeps the kernel's code size down.
+  const unsigned group = __activemask();
+  bool searching = !no_work;
+  // (scenes without box tests yield a leaf per walk step: all lanes are in lock-step anyway, no vote needed)
+  while (BOXES ? __any_sync(group, searching) : searching) {
     int leaf = -1;
-    while (i < n) {
-      const double* tv = sv.trav + i * 8;
-      const int2 gs = *reinterpret_cast<const int2*>(tv + 6);  // {geometry kind, skip}
-      if (BOXES && *reinterpret_cast<const int*>(tv + 7) && !slab_hit(br, tv)) { i = gs.y; continue; }
-      const int g = gs.x;
-      const int cur = i++;
-      if (g == OPTB_G_GROUP) continue;
-      if (g == OPTB_G_ASPHERE && n_parked < kPark) {
+    if (searching) {
+      while (i < n) {
+        const double* tv = sv.trav + i * 8;
+        const int2 gs = *reinterpret_cast<const int2*>(tv + 6);  // {geometry kind, skip}
+        if (BOXES && *reinterpret_cast<const int*>(tv + 7) && !slab_hit(br, tv)) { i = gs.y; continue; }
+        const int g = gs.x;
+        const int cur = i++;
+        if (g == OPTB_G_GROUP) continue;
+        if (ASPH && g == OPTB_G_ASPHERE && n_parked < kPark) {
 #pragma unroll
-        for (int k = 0; k < kPark; k++) if (k == n_parked) parked[k] = cur;
-        n_parked++;
-        continue;
+          for (int k = 0; k < kPark; k++) if (k == n_parked) parked[k] = cur;
+          n_parked++;
+          continue;
+        }
+        leaf = cur;
+        break;
       }
-      leaf = cur;
-      break;
-    }
-    if (leaf < 0) {
-      if (n_done >= n_parked) break;
+      if (leaf < 0) {
+        if (n_done < n_parked) {
 #pragma unroll
-      for (int k = 0; k < kPark; k++) if (k == n_done) leaf = parked[k];
-      n_done++;
+          for (int k = 0; k < kPark; k++) if (k == n_done) leaf = parked[k];
+          n_done++;
+        } else {
+          searching = false;
+        }
+      }
     }
-    hs.test_leaf(leaf, sv.ni + leaf * OPTB_NI_STRIDE, sv.nf + leaf * OPTB_NF_STRIDE);
+    if (leaf >= 0) hs.test_leaf(leaf, sv.ni + leaf * OPTB_NI_STRIDE, sv.nf + leaf * OPTB_NF_STRIDE);
   }
   best_t = hs.best_t; best_node = hs.best_node;
 }
 
-template <bool SMEM, bool SERIAL, bool BOXES>
+template <bool SMEM, bool SERIAL, bool BOXES, bool ASPH>
 __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -373,7 +385,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
           ring_get(a.w, ring + head % a.qcap, ray); head++;
           ray.root = root; ray.family = (int32_t)i; ray.pop = pops++;
           double t; int node;
-          closest_hit<BOXES>(a, sv, ray, true, t, node, c_tests);
+          closest_hit<BOXES, ASPH>(a, sv, ray, true, t, node, c_tests);
           c_pops++;
           const bool hit = node >= 0;
           const int32_t* ni = sv.ni + (hit ? node : 0) * OPTB_NI_STRIDE;
@@ -385,7 +397,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
           double ox, oy, oz, dx, dy, dz;
           to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
           Children ch;
-          interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
+          interact<ASPH>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
           for (int k = 0; k < ch.n; k++) {
             if (tail - head >= a.qcap) { atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_WORK_OVERFLOW); break; }
             Ray c = ray;
@@ -414,7 +426,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
         volatile double* pk = &s_park[0][threadIdx.x];
         pk[0 * kBlock] = ray.I; pk[1 * kBlock] = ray.wl; pk[2 * kBlock] = ray.qre;
         pk[3 * kBlock] = ray.qim; pk[4 * kBlock] = ray.pl; pk[5 * kBlock] = ray.n;
-        closest_hit<BOXES>(a, sv, ray, solo, t, node, c_tests);
+        closest_hit<BOXES, ASPH>(a, sv, ray, solo, t, node, c_tests);
         ray.I = pk[0 * kBlock]; ray.wl = pk[1 * kBlock]; ray.qre = pk[2 * kBlock];
         ray.qim = pk[3 * kBlock]; ray.pl = pk[4 * kBlock]; ray.n = pk[5 * kBlock];
       }
@@ -431,7 +443,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
       hit_leaf = ni[OPTB_NI_LEAF];
       double ox, oy, oz, dx, dy, dz;
       to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
-      interact(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
+      interact<ASPH>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
       nch = ch.n;
       if (nch == 1 && solo && (a.chain_len == 0 || chained + 1 < a.chain_len)) {
         // the root's alive set is this one ray: BFS order is trivially kept, continue in registers
@@ -641,7 +653,7 @@ struct optb_ctx {
 struct optb_scene {
   unsigned char* d_blob; uint32_t blob_bytes; SceneOff off;
   int n_nodes, n_leaves, n_mats, n_mons, n_caps; long long n_aux;
-  int max_children; int has_boxes;
+  int max_children; int has_boxes; int has_asph;
   bool in_smem; bool hist_smem; uint32_t smem_bytes;
 };
 
@@ -766,6 +778,7 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
     const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
     const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
     if (ni[OPTB_NI_AABB]) s->has_boxes = 1;
+    if (ni[OPTB_NI_GEOM] == OPTB_G_ASPHERE) s->has_asph = 1;
     int k = 0;
     switch (ni[OPTB_NI_INTER]) {
       case OPTB_I_MIRROR: k = (nf[OPTB_NF_REFL] > 0) + (nf[OPTB_NF_TRANS] > 0); break;
@@ -956,10 +969,15 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   }
   uint32_t smem = scene->in_smem ? scene->smem_bytes : (a.hist_smem ? scene->smem_bytes : 0);
   using Kern = void (*)(const TraceArgs);
+  // [smem][boxes][aspheres] for the parallel path; the family-serial path keeps one general variant per staging mode
   static const Kern table[2][2][2] = {
-      {{trace_kernel<false, false, false>, trace_kernel<false, false, true>}, {trace_kernel<false, true, false>, trace_kernel<false, true, true>}},
-      {{trace_kernel<true, false, false>, trace_kernel<true, false, true>}, {trace_kernel<true, true, false>, trace_kernel<true, true, true>}}};
-  Kern kern = table[scene->in_smem ? 1 : 0][serial ? 1 : 0][scene->has_boxes ? 1 : 0];
+      {{trace_kernel<false, false, false, false>, trace_kernel<false, false, false, true>},
+       {trace_kernel<false, false, true, false>, trace_kernel<false, false, true, true>}},
+      {{trace_kernel<true, false, false, false>, trace_kernel<true, false, false, true>},
+       {trace_kernel<true, false, true, false>, trace_kernel<true, false, true, true>}}};
+  static const Kern serial_table[2] = {trace_kernel<false, true, true, true>, trace_kernel<true, true, true, true>};
+  Kern kern = serial ? serial_table[scene->in_smem ? 1 : 0]
+                     : table[scene->in_smem ? 1 : 0][scene->has_boxes ? 1 : 0][scene->has_asph ? 1 : 0];
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
   int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem), "occupancy");

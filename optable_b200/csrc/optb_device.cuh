@@ -301,6 +301,7 @@ OPTB_DEV double sample_t(int i, double a, double b, double step) {
 }
 
 // intersect_point_local optical_component.py:151-233 for one leaf, local-frame ray. Returns t or -1.
+template <bool ASPH>
 OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
                                double ox, double oy, double oz, double dx, double dy, double dz, double len,
                                double t_beat = INFINITY) {
@@ -333,7 +334,7 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
   if (g == OPTB_G_SPHERE) {
 #pragma unroll
     for (int i = 0; i < 6; i++) bb[i] = p[2 + i];
-  } else if (g == OPTB_G_ASPHERE) {
+  } else if (ASPH && g == OPTB_G_ASPHERE) {
     bb[0] = p[6]; bb[1] = p[7]; bb[2] = -p[0]; bb[3] = p[0]; bb[4] = -p[0]; bb[5] = p[0];
   } else if (g == OPTB_G_CYL) {
     bb[0] = -p[0]; bb[1] = p[0]; bb[2] = -p[0]; bb[3] = p[0]; bb[4] = -p[1] / 2; bb[5] = p[1] / 2;
@@ -351,7 +352,7 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
   if (b >= a && a > t_beat) return -1.0;
   const double step = (b - a) / 9.0;
   // roots found by the sign scan, ascending in t (sub-intervals are visited in order)
-  if (g == OPTB_G_ASPHERE) {
+  if (ASPH && g == OPTB_G_ASPHERE) {
     // Scan first, solve after: the (expensive) root solve runs once for the whole warp instead of once per
     // sub-interval (lane efficiency 21 -> 31 of 32).
     const AsphF f(ni[OPTB_NI_AUX], p + 1, ox, oy, oz, dx, dy, dz);
@@ -447,6 +448,7 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
 }
 
 // Surface.normal at a local hit point
+template <bool ASPH>
 OPTB_DEV void surf_normal(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
                           double Px, double Py, double Pz, double& nx, double& ny, double& nz, double& roc_fd) {
   const int g = ni[OPTB_NI_GEOM];
@@ -454,7 +456,7 @@ OPTB_DEV void surf_normal(const SceneView& sv, const int32_t* __restrict__ ni, c
   roc_fd = INFINITY;
   if (g == OPTB_G_SPHERE) { double ir = 1.0 / p[0]; nx = Px * ir; ny = Py * ir; nz = Pz * ir; return; }
   if (g == OPTB_G_CYL) { double ir = 1.0 / p[0]; nx = Px * ir; ny = Py * ir; nz = 0.0; return; }
-  if (g == OPTB_G_ASPHERE) {
+  if (ASPH && g == OPTB_G_ASPHERE) {
     // central differences with h = 1e-4 * radius  surfaces.py:351-388
     double r = __dsqrt_rn(__dadd_rn(__dmul_rn(Py, Py), __dmul_rn(Pz, Pz)));
     double h = 1e-4 * p[0];
@@ -548,6 +550,7 @@ OPTB_DEV void dir_to_lab(const double* __restrict__ T, bool ortho, double lx, do
 }
 
 // interact_local bodies for the winning leaf. (ox..dz) is the ray in the leaf's local frame, t the hit parameter.
+template <bool ASPH>
 OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
                        const Ray& ray, double unit, double ox, double oy, double oz, double dx, double dy, double dz,
                        double t, Children& ch, const IndexCache& ic) {
@@ -579,7 +582,7 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
     return;
   }
   double nx, ny, nz, roc_fd;
-  surf_normal(sv, ni, nf, Px, Py, Pz, nx, ny, nz, roc_fd);
+  surf_normal<ASPH>(sv, ni, nf, Px, Py, Pz, nx, ny, nz, roc_fd);
   double dn = dot3(dx, dy, dz, nx, ny, nz);
   if (kind == OPTB_I_MIRROR) {  // BaseMirror :536-570, children [reflected, transmitted]
     double qre = ray.qre + t, qim = ray.qim;
