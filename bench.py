@@ -30,7 +30,7 @@ WORKLOAD = "c2_4f_telescope"
 BYTES_PER_INTERACTION = 208  # read + write one 104-B ray record per interaction (wavefront form)
 # fp64 flops per interaction of this workload, from the ncu instruction counts of profiles/ 
 E2E_EXTRA = {}
-FLOPS_PER_INTERACTION = 1534  # executed (2*DFMA + DMUL + DADD) / interactions, profiles/r1_trace_kernel_summary.md (r1e)
+FLOPS_PER_INTERACTION = 1390  # executed (2*DFMA + DMUL + DADD) / interactions, profiles/r1_trace_kernel_summary.md (r1f)
 
 
 def _workloads():
@@ -372,7 +372,7 @@ def finish(args, engine, flat, world, rank, n, inter_per_step, hits_per_step, la
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     achieved = BYTES_PER_INTERACTION * inter_per_step / (trace_ms * 1e-3) / 1e9
     # measured DRAM bytes per launch of this workload (ncu dram__bytes_read+write, profiles/r1_trace_kernel_summary.md)
-    traffic = 1.6825e9 if (args.workload == WORKLOAD and n == 10_000_000) else None
+    traffic = 1.6686e9 if (args.workload == WORKLOAD and n == 10_000_000) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "trace_kernel", "kernel_ms": trace_ms,
                 "note": "kernel is FP64-pipe bound, not HBM bound: see roofline_fp64 and DESIGN.md"}
