@@ -6,9 +6,10 @@
 //                     shared memory with a TMA bulk copy (cp.async.bulk + mbarrier). A root whose alive set
 //                     is a single ray keeps bouncing in registers (closest hit -> physics -> monitors ->
 //                     next bounce); split interactions park their children in a sparse slot pair.
-//   tile_sums/scan_sums/scatter   ordered stream compaction of the children into the next wavefront
-//                     (order = reference BFS order, which the pop cap of optical_table.py:86-97 needs).
+//   tile_sums/scan_sums/slots     ordered, index-only stream compaction: the list of occupied child slots in
+//                     reference BFS order (which the pop cap of optical_table.py:86-97 needs); rays are not moved.
 //   mark_kernel       first/last wavefront index of every root (rank of a ray inside its root's generation).
+//   sort_prep + cub radix sort    processing order of a generation by coherence key (storage order stays BFS).
 // Segments and monitor rows are appended with warp-aggregated atomics and carry their (root, pop) key.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -55,6 +56,7 @@ struct TraceArgs {
   long long n_in; const unsigned int* n_in_dev;  // n_in_dev overrides when non-null
   const uint32_t* gen_first; const uint32_t* gen_last;
   const uint32_t* perm;  // processing order of the wavefront (sorted by coherence key), or null
+  const uint32_t* slot;  // wavefront index (reference order, dense) -> slot of the ray in the sparse buffer `w`
   // split output
   RayBuf c; uint8_t* nchild;
   // params
@@ -118,16 +120,19 @@ OPTB_DEV void load_ray(const TraceArgs& a, long long i, Ray& r, bool& solo, uint
     r.family = s.family ? s.family[i] : (int32_t)r.root;
     solo = true; gcount = 1;
   } else {
+    // Children stay where the previous generation's kernel wrote them (slot 2*parent + k of the sparse buffer);
+    // `slot` lists the occupied slots in reference order, so nothing is copied between generations.
     const RayBuf& w = a.w;
-    r.ox = w.f[0][i]; r.oy = w.f[1][i]; r.oz = w.f[2][i];
-    r.dx = w.f[3][i]; r.dy = w.f[4][i]; r.dz = w.f[5][i];
-    r.I = w.f[6][i]; r.wl = w.f[7][i]; r.qre = w.f[8][i]; r.qim = w.f[9][i];
-    r.pl = w.f[10][i]; r.n = w.f[11][i]; r.len = w.f[12][i];
-    r.flags = w.flags[i]; r.root = w.root[i]; r.family = w.family[i];
+    const long long s = a.slot[i];
+    r.ox = w.f[0][s]; r.oy = w.f[1][s]; r.oz = w.f[2][s];
+    r.dx = w.f[3][s]; r.dy = w.f[4][s]; r.dz = w.f[5][s];
+    r.I = w.f[6][s]; r.wl = w.f[7][s]; r.qre = w.f[8][s]; r.qim = w.f[9][s];
+    r.pl = w.f[10][s]; r.n = w.f[11][s]; r.len = w.f[12][s];
+    r.flags = w.flags[s]; r.root = w.root[s]; r.family = w.family[s];
     uint32_t first = a.gen_first[r.root], last = a.gen_last[r.root];
     gcount = last - first + 1;
     solo = (gcount == 1);
-    r.pop = w.pop[i] + (uint32_t)(i - first);  // pop_base of this generation + rank inside the root
+    r.pop = w.pop[s] + (uint32_t)(i - first);  // pop_base of this generation + rank inside the root
   }
 }
 
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __
 
     Ray ray; bool solo; uint32_t gcount;
     load_ray(a, i, ray, solo, gcount);
-    const uint32_t pop_base_next = a.gen0 ? 0u : (a.w.pop[i] + gcount);
+    const uint32_t pop_base_next = a.gen0 ? 0u : (ray.pop - (uint32_t)(i - a.gen_first[ray.root]) + gcount);
     int nch = 0;
     int chained = 0;
     int hit_leaf = 0;
@@ -544,11 +549,11 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restric
   }
 }
 
-// Thread t of a block handles parents base + sub*256 + t for sub = 0..7: reads of the sparse child slots and
-// writes of the packed wavefront are both (nearly) coalesced; a running carry keeps the global order.
-__global__ void __launch_bounds__(kScanBlock) scatter_kernel(const uint8_t* __restrict__ nchild, long long n,
-                                                             const unsigned int* __restrict__ tile_base, RayBuf c, RayBuf w,
-                                                             const Header* hdr) {
+// Ordered compaction, index only: the k-th child of wavefront entry i sits in slot 2i+k of the sparse buffer; this
+// writes the list of occupied slots in reference (BFS) order. Thread t of a block handles entries base + sub*256 + t.
+__global__ void __launch_bounds__(kScanBlock) slots_kernel(const uint8_t* __restrict__ nchild, long long n,
+                                                           const unsigned int* __restrict__ tile_base,
+                                                           uint32_t* __restrict__ slot_next, const Header* hdr) {
   __shared__ unsigned int s_warp[kScanBlock / 32];
   __shared__ unsigned int s_carry;
   if (hdr->n_next == 0) return;
@@ -568,26 +573,20 @@ __global__ void __launch_bounds__(kScanBlock) scatter_kernel(const uint8_t* __re
     unsigned int woff = 0, total = 0;
     for (int k = 0; k < kScanBlock / 32; k++) { if (k < wid) woff += s_warp[k]; total += s_warp[k]; }
     const unsigned int off = s_carry + woff + incl - mine;
-    for (unsigned int j = 0; j < mine; j++) {
-      const long long src = 2 * i + j, dst = (long long)off + j;
-#pragma unroll
-      for (int f = 0; f < kRayF64; f++) w.f[f][dst] = c.f[f][src];
-      w.flags[dst] = c.flags[src]; w.root[dst] = c.root[src]; w.pop[dst] = c.pop[src]; w.family[dst] = c.family[src];
-      w.key[dst] = c.key[src];
-    }
+    for (unsigned int j = 0; j < mine; j++) slot_next[off + j] = (uint32_t)(2 * i + j);
     __syncthreads();
     if (threadIdx.x == 0) s_carry += total;
     __syncthreads();
   }
 }
 
-__global__ void mark_kernel(const uint32_t* __restrict__ root, const Header* hdr, uint32_t* __restrict__ gen_first,
-                            uint32_t* __restrict__ gen_last) {
+__global__ void mark_kernel(const uint32_t* __restrict__ root, const uint32_t* __restrict__ slot, const Header* hdr,
+                            uint32_t* __restrict__ gen_first, uint32_t* __restrict__ gen_last) {
   long long n = hdr->n_next;
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
-    uint32_t r = root[j];
-    if (j == 0 || root[j - 1] != r) gen_first[r] = (uint32_t)j;
-    if (j == n - 1 || root[j + 1] != r) gen_last[r] = (uint32_t)j;
+    uint32_t r = root[slot[j]];
+    if (j == 0 || root[slot[j - 1]] != r) gen_first[r] = (uint32_t)j;
+    if (j == n - 1 || root[slot[j + 1]] != r) gen_last[r] = (uint32_t)j;
   }
 }
 
@@ -606,13 +605,13 @@ __global__ void fam_scatter_kernel(const int32_t* __restrict__ family, long long
 
 // Sort input of one generation: identity permutation + the coherence key, with "this root has a single live ray"
 // (it will chain many pops in registers) as the top bit so that one-pop rays and chaining rays do not share warps.
-__global__ void sort_prep_kernel(uint32_t* __restrict__ idx, uint32_t* __restrict__ key, const uint32_t* __restrict__ root,
-                                 long long n, int key_bits) {
+__global__ void sort_prep_kernel(uint32_t* __restrict__ idx, uint32_t* __restrict__ key_dense, const uint32_t* __restrict__ key,
+                                 const uint32_t* __restrict__ root, const uint32_t* __restrict__ slot, long long n, int key_bits) {
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
     idx[j] = (uint32_t)j;
-    const uint32_t r = root[j];
-    const bool solo = (j == 0 || root[j - 1] != r) && (j == n - 1 || root[j + 1] != r);
-    key[j] = (key[j] & ((1u << key_bits) - 1u)) | ((solo ? 1u : 0u) << key_bits);
+    const uint32_t s = slot[j], r = root[s];
+    const bool solo = (j == 0 || root[slot[j - 1]] != r) && (j == n - 1 || root[slot[j + 1]] != r);
+    key_dense[j] = (key[s] & ((1u << key_bits) - 1u)) | ((solo ? 1u : 0u) << key_bits);
   }
 }
 
@@ -813,7 +812,7 @@ extern "C" int optb_scene_destroy(optb_ctx* ctx, optb_scene* s) {
 
 namespace {
 struct WsLayout {
-  size_t hdr, w, c, nchild, gen_first, gen_last, sums, iota, perm, key_sorted, cub, cub_bytes, total;
+  size_t hdr, w, c, nchild, gen_first, gen_last, sums, iota, perm, key_sorted, key_dense, slot_a, slot_b, cub, cub_bytes, total;
   long long cap;  // wavefront capacity (rays)
 };
 size_t raybuf_bytes(long long cap) { return align_up((size_t)cap * 8, 256) * kRayF64 + align_up((size_t)cap * 4, 256) * 5; }
@@ -823,8 +822,11 @@ WsLayout ws_layout(long long n_rays, long long max_live, bool split) {
   L.hdr = o; o += align_up(sizeof(Header), 256);
   L.cap = split ? std::max(max_live, n_rays) : 0;
   if (split) {
-    L.w = o; o += raybuf_bytes(L.cap);
+    L.w = o; o += raybuf_bytes(2 * L.cap);  // two sparse child buffers, used alternately as source and destination
     L.c = o; o += raybuf_bytes(2 * L.cap);
+    L.slot_a = o; o += align_up((size_t)L.cap * 4, 256);
+    L.slot_b = o; o += align_up((size_t)L.cap * 4, 256);
+    L.key_dense = o; o += align_up((size_t)L.cap * 4, 256);
     L.nchild = o; o += align_up((size_t)L.cap, 256);
     L.gen_first = o; o += align_up((size_t)n_rays * 4, 256);
     L.gen_last = o; o += align_up((size_t)n_rays * 4, 256);
@@ -961,7 +963,7 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   a.root_base = root_base;
   a.has_boxes = scene->has_boxes;
   if (split) {
-    a.w = make_raybuf(ws + L.w, cap);
+    a.w = make_raybuf(ws + L.w, 2 * cap);
     a.c = make_raybuf(ws + L.c, 2 * cap);
     a.nchild = ws + L.nchild;
     a.gen_first = (uint32_t*)(ws + L.gen_first);
@@ -1013,9 +1015,10 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     if (split && !a.gen0 && n_in >= 2048 && n_in < 0x7fffffffll) {
       uint32_t* iota = (uint32_t*)(ws + L.iota);
       uint32_t* perm = (uint32_t*)(ws + L.perm);
-      sort_prep_kernel<<<std::min(full_grid * 4, (int)((n_in + 255) / 256)), 256, 0, st>>>(iota, a.w.key, a.w.root, n_in, key_bits);
+      uint32_t* key_dense = (uint32_t*)(ws + L.key_dense);
+      sort_prep_kernel<<<std::min(full_grid * 4, (int)((n_in + 255) / 256)), 256, 0, st>>>(iota, key_dense, a.w.key, a.w.root, a.slot, n_in, key_bits);
       size_t tb = L.cub_bytes;
-      CK(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, (const uint32_t*)a.w.key, (uint32_t*)(ws + L.key_sorted),
+      CK(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, (const uint32_t*)key_dense, (uint32_t*)(ws + L.key_sorted),
                                          (const uint32_t*)iota, perm, (int)n_in, 0, key_bits + 1, st), "radix sort");
       a.perm = perm;
       launches += 4;
@@ -1033,8 +1036,12 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     unsigned int* sums = (unsigned int*)(ws + L.sums);
     tile_sums_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, n_in, sums);
     scan_sums_kernel<<<1, 1024, 0, st>>>(sums, ntiles, hdr, a.counters, (unsigned int)std::min<long long>(cap, 0xffffffffll));
-    scatter_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, n_in, sums, a.c, a.w, hdr);
-    mark_kernel<<<std::min(full_grid * 2, std::max(1, (int)((2 * n_in + 255) / 256))), 256, 0, st>>>(a.w.root, hdr, (uint32_t*)a.gen_first, (uint32_t*)a.gen_last);
+    // the children just written to a.c become the next generation's source; the other buffer is free again
+    uint32_t* slot_next = (uint32_t*)(ws + ((gens & 1) ? L.slot_a : L.slot_b));
+    slots_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, n_in, sums, slot_next, hdr);
+    mark_kernel<<<std::min(full_grid * 2, std::max(1, (int)((2 * n_in + 255) / 256))), 256, 0, st>>>(a.c.root, slot_next, hdr, (uint32_t*)a.gen_first, (uint32_t*)a.gen_last);
+    std::swap(a.w, a.c);
+    a.slot = slot_next;
     launches += 4;
     CK(cudaMemcpyAsync(ctx->h_hdr, hdr, sizeof(Header), cudaMemcpyDeviceToHost, st), "read header");
     CK(cudaStreamSynchronize(st), "sync generation");
