@@ -128,3 +128,19 @@ def test_scene_upload_rejects_malformed_tables():
         with pytest.raises(BackendError):
             engine.upload(bad)
     engine.upload(flat).close()
+
+
+def test_edge_cases_empty_inputs_and_long_chains():
+    """Empty ray list, empty table, one ray bouncing 1e5 times in a closed cavity (the ripa example's pop budget)."""
+    table = ob.OpticalTable()
+    assert table.ray_tracing([]) == [] and table.rays == []
+    out = table.ray_tracing([ob.Ray([0, 0, 0], [1, 0, 0])])          # nothing to hit: the ray itself comes back
+    assert len(out) == 1 and out[0].alive and out[0].length is None
+    sc = scenes.cavity(ob, 0.0, 0.0, gaussian=True)
+    t2 = ob.OpticalTable()
+    t2.add_components(sc.components)
+    segs = t2.ray_tracing(sc.rays, perfomance_limit={"max_trace_num": 1e5})
+    assert len(segs) == 100000 and all(s.length is not None for s in segs[:10])
+    assert segs[-1].intensity == 0.0 or segs[-1].intensity < 1e-300   # 0.9^1e5 underflows, no cutoff in the reference
+    L = 10 * 4 / 3
+    assert segs[-1]._pathlength == pytest.approx(99999 * L - 2, rel=1e-9)
