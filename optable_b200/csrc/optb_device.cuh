@@ -72,10 +72,11 @@ OPTB_DEV bool slab(double ox, double oy, double oz, double dx, double dy, double
     if (fabs(d[ax]) <= 1e-8) {  // np.isclose(d, 0.0)
       if (o[ax] < bmin || o[ax] > bmax) { t1 = 1.0; t2 = 0.0; }
     } else {
-      double inv = 1.0 / d[ax];
-      double ta = (bmin - o[ax]) * inv, tb = (bmax - o[ax]) * inv;
-      t1 = ta < tb ? (ta > t1 ? ta : t1) : (tb > t1 ? tb : t1);
-      t2 = ta < tb ? (tb < t2 ? tb : t2) : (ta < t2 ? ta : t2);
+      const double inv = 1.0 / d[ax];
+      const bool fwd = d[ax] > 0.0;  // min(ta, tb) / max(ta, tb) picked by the sign of d (bmin <= bmax)
+      const double tn = ((fwd ? bmin : bmax) - o[ax]) * inv, tf = ((fwd ? bmax : bmin) - o[ax]) * inv;
+      t1 = tn > t1 ? tn : t1;
+      t2 = tf < t2 ? tf : t2;
     }
   }
   t1o = t1; t2o = t2;
@@ -424,25 +425,31 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
     if (B == 0.0) return -1.0;
     lo = hi = -Cc / (2.0 * B);
   }
-  double ta = a, ga = fma(fma(A, a, 2.0 * B), a, Cc);
+  // ten sample signs as bit masks (independent evaluations), then the sub-intervals with a sign change in order
+  unsigned pos = 0u, neg = 0u;
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const double ts = sample_t(i, a, b, step);
+    const double gv = fma(fma(A, ts, 2.0 * B), ts, Cc);
+    pos |= (gv > 0.0 ? 1u : 0u) << i;
+    neg |= (gv < 0.0 ? 1u : 0u) << i;
+  }
+  unsigned chg = ((pos & (neg >> 1)) | (neg & (pos >> 1))) & 0x1ffu;  // bit i: g(ts_i) * g(ts_i+1) < 0
+  const bool asc = (b >= a);
   double best = -1.0;
-  for (int i = 1; i < 10; i++) {
-    double tb = sample_t(i, a, b, step);
-    double gb = fma(fma(A, tb, 2.0 * B), tb, Cc);
-    if (ga * gb < 0) {
-      // exactly one root of g inside this sub-interval: entering (g: + -> -) is `lo`, leaving is `hi`
-      double r;
-      if (A != 0.0) r = ((ga > 0) == (tb > ta)) ? lo : hi;
-      else r = lo;
-      if (r >= 1e-9 && r <= len) {
-        double Px = fma(r, dx, ox), Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
-        if (curved_within(sv, g, ni, p, Px, Py, Pz)) {
-          if (b >= a) return r;
-          if (best < 0 || r < best) best = r;
-        }
+  while (chg) {
+    const int i = __ffs(chg) - 1;
+    chg &= chg - 1u;
+    // exactly one root of g inside this sub-interval: entering (g: + -> -, seen along increasing t) is `lo`
+    const bool ga_pos = (pos >> i) & 1u;
+    const double r = (A != 0.0) ? ((ga_pos == asc) ? lo : hi) : lo;
+    if (r >= 1e-9 && r <= len) {
+      double Px = fma(r, dx, ox), Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
+      if (curved_within(sv, g, ni, p, Px, Py, Pz)) {
+        if (asc) return r;
+        if (best < 0 || r < best) best = r;
       }
     }
-    ta = tb; ga = gb;
   }
   return best;
 }
