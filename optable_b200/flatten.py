@@ -418,36 +418,34 @@ def pack_rays(rays):
     length (None -> +inf), alive, qo (None -> flag), _pathlength, n, _id, unit.
     """
     n = len(rays)
-    out = {k: np.empty(n, dtype=np.float64) for k in A.RAY_F64}
-    flags = np.zeros(n, dtype=np.uint32)
-    family = np.zeros(n, dtype=np.int32)
+    f64 = lambda it: np.fromiter(it, dtype=np.float64, count=n)
+    O = np.array([r.origin for r in rays], dtype=np.float64).reshape(n, 3)
+    D = np.array([r._direction for r in rays], dtype=np.float64).reshape(n, 3)
+    out = {"ox": O[:, 0].copy(), "oy": O[:, 1].copy(), "oz": O[:, 2].copy(),
+           "dx": D[:, 0].copy(), "dy": D[:, 1].copy(), "dz": D[:, 2].copy(),
+           "intensity": f64(r.intensity for r in rays),
+           "wavelength": f64((r.wavelength if r.wavelength is not None else 0.0) for r in rays)}
+    qs = [r.qo for r in rays]
+    hasq = np.fromiter((q is not None for q in qs), dtype=bool, count=n)
+    qc = np.fromiter((0j if q is None else q for q in qs), dtype=np.complex128, count=n)
+    out["q_re"], out["q_im"] = qc.real.copy(), qc.imag.copy()
+    out["pathlength"] = f64(r._pathlength for r in rays)
+    out["n_medium"] = f64(r.n for r in rays)
+    out["length"] = f64((math.inf if r.length is None else r.length) for r in rays)
+    out = {k: out[k] for k in A.RAY_F64}
+    alive = np.fromiter((bool(r.alive) for r in rays), dtype=bool, count=n)
+    flags = (np.where(hasq, A.RF_HASQ, 0) | np.where(alive, A.RF_ALIVE, 0)).astype(np.uint32)
     fam_index, fam_ids = {}, []
-    units = set()
+    fam = [0] * n
     for i, r in enumerate(rays):
-        o, d = r.origin, r._direction
-        out["ox"][i], out["oy"][i], out["oz"][i] = o[0], o[1], o[2]
-        out["dx"][i], out["dy"][i], out["dz"][i] = d[0], d[1], d[2]
-        out["intensity"][i] = r.intensity
-        out["wavelength"][i] = r.wavelength if r.wavelength is not None else 0.0
-        q = r.qo
-        f = 0
-        if q is not None:
-            out["q_re"][i], out["q_im"][i] = q.real, q.imag
-            f |= A.RF_HASQ
-        else:
-            out["q_re"][i] = out["q_im"][i] = 0.0
-        if r.alive:
-            f |= A.RF_ALIVE
-        flags[i] = f
-        out["pathlength"][i] = r._pathlength
-        out["n_medium"][i] = r.n
-        out["length"][i] = math.inf if r.length is None else r.length
         rid = r._id
-        if rid not in fam_index:
-            fam_index[rid] = len(fam_ids)
+        j = fam_index.get(rid)
+        if j is None:
+            j = fam_index[rid] = len(fam_ids)
             fam_ids.append(rid)
-        family[i] = fam_index[rid]
-        units.add(float(r.unit))
+        fam[i] = j
+    family = np.array(fam, dtype=np.int32).reshape(n)
+    units = {float(r.unit) for r in rays}
     if len(units) > 1:
         raise FlattenError("rays with different .unit in one batch are not supported")
     out["flags"], out["family"] = flags, family

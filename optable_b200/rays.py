@@ -6,7 +6,6 @@ exist as Python objects.
 """
 from __future__ import annotations
 
-import copy as _copy
 from typing import List
 
 import numpy as np
@@ -75,9 +74,11 @@ class Ray(Vector):
 
     def copy(self, **overrides):
         """Same `_id`, fresh arrays. (The generic deepcopy is not needed: a Ray owns only two small arrays.)"""
-        twin = _copy.copy(self)
-        twin.origin = np.array(self.origin, dtype=float)
-        twin._direction = np.array(self._direction, dtype=float)
+        twin = object.__new__(type(self))
+        fields = twin.__dict__
+        fields.update(self.__dict__)
+        fields["origin"] = np.array(self.origin, dtype=float)
+        fields["_direction"] = np.array(self._direction, dtype=float)
         for key, value in overrides.items():
             setattr(twin, key, value)
         return twin

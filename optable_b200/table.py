@@ -24,17 +24,71 @@ from .monitors import Monitor
 from .rays import Ray
 
 
-def _segment_object(root_ray, o, d, length, alive, intensity, q, hasq, pathlength, n):
-    seg = _copy.copy(root_ray)
-    seg.origin = np.array(o, dtype=float)
-    seg._direction = np.array(d, dtype=float)
-    seg.length = None if math.isinf(length) else float(length)
-    seg.alive = bool(alive)
-    seg.intensity = float(intensity)
-    seg.qo = complex(q) if hasq else None
-    seg._pathlength = float(pathlength)
-    seg._n = float(n)
-    return seg
+_CONST_MATERIALS = {}
+
+
+def _const_material(n):
+    """One shared constant-index Material per distinct value (what `Ray._n = n` would build for every segment)."""
+    m = _CONST_MATERIALS.get(n)
+    if m is None:
+        from .materials import Material
+
+        if len(_CONST_MATERIALS) > 4096:
+            _CONST_MATERIALS.clear()
+        m = _CONST_MATERIALS[n] = Material("Constant", n=n)
+    return m
+
+
+def _segment_objects(rays, out):
+    """Segment rows -> ray objects: a shallow copy of the initial ray (keeps `_id`, wavelength, user attributes)
+    with the traced fields overwritten. Columns are converted to Python scalars in bulk; for this package's own
+    `Ray` the copy is a `__dict__` update instead of the generic copy protocol."""
+    n = len(out["seg_root"])
+    if not n:
+        return []
+    O = np.stack((out["seg_ox"], out["seg_oy"], out["seg_oz"]), 1)
+    D = np.stack((out["seg_dx"], out["seg_dy"], out["seg_dz"]), 1)
+    flags = out["seg_flags"]
+    root = out["seg_root"].tolist()
+    inf = np.isinf(out["seg_length"])
+    length = out["seg_length"].tolist()
+    alive = ((flags & A.RF_ALIVE) != 0).tolist()
+    hasq = ((flags & A.RF_HASQ) != 0).tolist()
+    inten = out["seg_intensity"].tolist()
+    q = (out["seg_q_re"] + 1j * out["seg_q_im"]).tolist()
+    pl = out["seg_pathlength"].tolist()
+    nmed = out["seg_n"].tolist()
+    if inf.any():
+        for k in np.nonzero(inf)[0].tolist():
+            length[k] = None
+    segs = [None] * n
+    new = object.__new__
+    for k in range(n):
+        src = rays[root[k]]
+        if type(src) is Ray:
+            seg = new(Ray)
+            d = seg.__dict__
+            d.update(src.__dict__)
+            d["origin"] = O[k].copy()
+            d["_direction"] = D[k].copy()
+            d["length"] = length[k]
+            d["alive"] = alive[k]
+            d["intensity"] = inten[k]
+            d["qo"] = q[k] if hasq[k] else None
+            d["_pathlength"] = pl[k]
+            d["_n"] = _const_material(nmed[k])
+        else:  # any other ray class (the reference's own after `install`): generic copy + attribute protocol
+            seg = _copy.copy(src)
+            seg.origin = O[k].copy()
+            seg._direction = D[k].copy()
+            seg.length = length[k]
+            seg.alive = alive[k]
+            seg.intensity = inten[k]
+            seg.qo = q[k] if hasq[k] else None
+            seg._pathlength = pl[k]
+            seg._n = nmed[k]
+        segs[k] = seg
+    return segs
 
 
 def trace_table(table, rays, perfomance_limit=None, engine=None):
@@ -60,15 +114,7 @@ def trace_table(table, rays, perfomance_limit=None, engine=None):
     if int(out["counters"][A.C_STATUS]) & A.ST_CAP_ORDER:
         raise RuntimeError("an interact cap (max_interact_count) bound while several rays of one family were in "
                            "flight: the reference result depends on sequential order; not supported on the device")
-    n = len(out["seg_root"])
-    flags = out["seg_flags"]
-    segs = [None] * n
-    for k in range(n):
-        segs[k] = _segment_object(
-            rays[int(out["seg_root"][k])],
-            (out["seg_ox"][k], out["seg_oy"][k], out["seg_oz"][k]), (out["seg_dx"][k], out["seg_dy"][k], out["seg_dz"][k]),
-            out["seg_length"][k], flags[k] & A.RF_ALIVE, out["seg_intensity"][k],
-            complex(out["seg_q_re"][k], out["seg_q_im"][k]), flags[k] & A.RF_HASQ, out["seg_pathlength"][k], out["seg_n"][k])
+    segs = _segment_objects(rays, out)
     # segment lookup for monitor rows: rows are (root, pop)-sorted, so is the segment list
     if len(out["hit_root"]):
         seg_key = out["seg_root"].astype(np.int64) << 32 | out["seg_pop"].astype(np.int64)

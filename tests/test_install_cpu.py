@@ -87,3 +87,46 @@ def test_installed_backend_equals_original_method(name):
     leaves_w, leaves_g = RH._leaves(ta.components, []), RH._leaves(tb.components, [])
     for cw, cg in zip(leaves_w, leaves_g):
         assert sorted(cw._interact_count.values()) == sorted(cg._interact_count.values()) or cw.max_interact_count is None
+
+
+@pytest.mark.parametrize("name", ["gaussian_beam", "chromatic", "telescope_4f", "prism_refl", "misc_components"])
+def test_own_classes_through_trace_table_equal_reference(name):
+    """This package's own scene classes + `OpticalTable.ray_tracing` host logic (ray packing, the `Ray` fast path
+    of the segment builder, columnar monitors), oracle engine in place of the device: segment for segment equal
+    to the reference's method on the reference's classes."""
+    import optable_b200 as ob
+    from optable_b200.table import trace_table
+
+    ref = RH.load_reference()
+    a, b = scenes.REGISTRY[name](ref), scenes.REGISTRY[name](ob)
+    ta, tb = ref.OpticalTable(), ob.OpticalTable()
+    for t, sc in ((ta, a), (tb, b)):
+        t.add_components(sc.components)
+        t.add_monitors(sc.monitors)
+    ta.ray_tracing(a.rays, perfomance_limit=a.limit)
+    before = [(_fields(r), dict(r.__dict__)) for r in b.rays]
+    segs = trace_table(tb, list(b.rays), b.limit, engine=OracleEngine())
+    assert len(segs) == len(ta.rays)
+    for rw, rg in zip(ta.rays, segs):
+        fw, fg = _fields(rw), _fields(rg)
+        assert type(rg) is ob.Ray
+        assert parity._rel_vec(fw[0], fg[0], 1.0) <= 1e-9 and parity._rel_vec(fw[1], fg[1], 1.0) <= 1e-9
+        assert (fw[2] is None) == (fg[2] is None) and (fw[2] is None or abs(fw[2] - fg[2]) <= 1e-9 * max(abs(fw[2]), 1e-3))
+        assert fw[3] == fg[3] and fw[4] == pytest.approx(fg[4], rel=1e-9) and fw[5] == fg[5]
+        assert (fw[6] is None) == (fg[6] is None) and (fw[6] is None or abs(fw[6] - fg[6]) <= 1e-9 * abs(fw[6]))
+        assert fw[7] == pytest.approx(fg[7], rel=1e-9, abs=1e-12) and fw[8] == pytest.approx(fg[8], rel=1e-12)
+        assert isinstance(rg.length, (float, type(None))) and isinstance(rg.alive, bool) and isinstance(rg.intensity, float)
+    # every segment keeps the `_id` of the initial ray it descends from, and owns its arrays
+    ids = {r._id for r in b.rays}
+    assert {s._id for s in segs} <= ids
+    segs[0].origin[0] += 1.0
+    assert all(s.origin[0] != segs[0].origin[0] or s is segs[0] for s in segs[1:2])
+    # inputs untouched
+    for r, (f0, d0) in zip(b.rays, before):
+        f1 = _fields(r)
+        assert np.array_equal(f0[0], f1[0]) and np.array_equal(f0[1], f1[1]) and f0[2:] == f1[2:]
+    for mw, mg in zip(ta.monitors, tb.monitors):
+        assert len(mw._data_raw) == mg.ndata
+        if mw._data_raw:
+            np.testing.assert_allclose(mg.get_yList(sort="YZ"), mw.get_yList(sort="YZ"), rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(mg.get_tYList(sort="YZ"), mw.get_tYList(sort="YZ"), rtol=1e-9, atol=1e-12)
