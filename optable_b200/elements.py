@@ -71,6 +71,12 @@ class OpticalComponent(Vector):
         self.origin = pivot(self.origin, R, localpoint)
         return self
 
+    def gather_components(self, avoid_flatten_classname=(), ignore_classname=()):
+        """Flat description rows of this component tree for the CSV export (optical_component.py:386-426)."""
+        from .export import component_rows
+
+        return component_rows(self, avoid_flatten_classname, ignore_classname)
+
     def point_to_lab_coordinates(self, point_local):
         return self.transform_matrix @ np.asarray(point_local, dtype=float) + self.origin
 

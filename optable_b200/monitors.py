@@ -53,10 +53,33 @@ class Monitor(OpticalComponent):
         self._sorted_cache = {}
         self._updated = True
 
-    def record(self, rays):
-        """Segment-vs-monitor test for an explicit list of segments. The arithmetic only exists on the device;
-        use OpticalTable.ray_tracing (monitors are filled during the trace)."""
-        raise NotImplementedError("Monitor.record runs on the device as part of OpticalTable.ray_tracing")
+    def record(self, rays, engine=None):
+        """Test an explicit list of rays/segments against this monitor and append the hits (monitor.py:183-193).
+        `OpticalTable.ray_tracing` fills monitors during the trace; this entry point is for segments that come
+        from somewhere else. It is the same device code: the rays are traced through a scene that holds no
+        component, where every ray is popped once, hits nothing and is tested against the monitor over its own
+        `length`. Rows reference the ray objects passed in, like the reference's."""
+        from .backend import Engine
+        from .flatten import FlatScene, pack_rays
+
+        rays = list(rays)
+        self._updated = True
+        if not rays:
+            return
+        engine = engine or Engine.get()
+        arrs, fam_ids, unit = pack_rays(rays)
+        scene = engine.upload(FlatScene([], [self]))
+        try:
+            out = engine.trace_arrays(scene, arrs, max_trace_num=1, unit=unit, n_families=len(fam_ids))
+        finally:
+            scene.close()
+        src = [rays[k] for k in out["hit_root"].tolist()]
+        self._extend(np.stack([out["hit_px"], out["hit_py"], out["hit_pz"]], 1), out["hit_intensity"], out["hit_t"],
+                     np.stack([out["hit_dx"], out["hit_dy"], out["hit_dz"]], 1),
+                     out["hit_q_re"] + 1j * out["hit_q_im"], [r._id for r in src], src)
+
+    def interact_local(self, ray):
+        return [ray]  # a monitor never alters a ray (monitor.py:174-175)
 
     # -- the reference's views --------------------------------------------------------------------------
     @property
@@ -161,6 +184,15 @@ class Monitor(OpticalComponent):
         q = self._col(self._q, "YZ") + self.get_tList()
         towards = self.get_directionList() @ self.normal > 0
         return np.where(towards, -np.real(q), np.real(q))
+
+    def get_beam_waist(self):
+        """Gaussian beam radius w at each hit, from q propagated to the hit (monitor.py:218-225; the reference
+        reads a non-existent `rList` there and raises AttributeError, the intended quantity is returned here).
+        Needs the segment objects (wavelength and index are per ray)."""
+        out = []
+        for r, t in zip(self.get_rays(), self.get_tList()):
+            out.append(r.waist(r.q_at_z(t)))
+        return np.array(out)
 
     def get_delta_pos(self):
         y, z = self.yList, self.zList

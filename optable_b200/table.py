@@ -266,6 +266,32 @@ class OpticalTable:
                        options={"xatol": 1e-5, "maxiter": 50})
         return tuple(res.x)
 
+    # ---- exports (optical_table.py:447-523) ----------------------------------------------------------
+    def gather_rays_csv(self):
+        from .export import ray_rows
+
+        return ray_rows(self.rays)
+
+    def gather_components(self, avoid_flatten_classname: List = [], ignore_classname: List = []) -> List[dict]:
+        from .export import component_rows
+
+        rows = []
+        for c in self.components:
+            rows.extend(component_rows(c, avoid_flatten_classname, ignore_classname))
+        return rows
+
+    def export_rays_csv(self, filename: str):
+        from .export import write_csv
+
+        print(f"Exporting rays to {filename} ...")
+        write_csv(filename, self.gather_rays_csv())
+
+    def export_components_csv(self, filename: str, avoid_flatten_classname: List = [], ignore_classname: List = []):
+        from .export import write_csv
+
+        print(f"Exporting components to {filename} ...")
+        write_csv(filename, self.gather_components(avoid_flatten_classname, ignore_classname))
+
     def trace_bundle(self, bundle, perfomance_limit=None, **kw):
         """Tensor entry point: see optable_b200.bundle.trace_bundle."""
         from .bundle import trace_bundle

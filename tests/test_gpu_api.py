@@ -144,3 +144,28 @@ def test_edge_cases_empty_inputs_and_long_chains():
     assert segs[-1].intensity == 0.0 or segs[-1].intensity < 1e-300   # 0.9^1e5 underflows, no cutoff in the reference
     L = 10 * 4 / 3
     assert segs[-1]._pathlength == pytest.approx(99999 * L - 2, rel=1e-9)
+
+
+def test_monitor_record_explicit_segments():
+    """Monitor.record(list) through the device (empty scene, one pop per ray) against the oracle's rows."""
+    from optable_b200.flatten import FlatScene, pack_rays
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(11)
+    mon = ob.Monitor(origin=[5, 0.2, -0.1], width=2, height=1.5).RotZ(0.3).RotY(-0.2)
+    rays = []
+    for k in range(500):
+        d = [1.0 if k % 7 else -1.0, rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3)]
+        kw = {"length": float(rng.uniform(2.0, 9.0))} if k % 3 == 0 else {}
+        rays.append(ob.Ray(rng.uniform(-1, 1, 3), d, wavelength=780e-7, alive=bool(k % 5), w0=0.01 if k % 2 else None, **kw))
+    mon.record(rays)
+    arrs, fam, unit = pack_rays(rays)
+    want = O.trace(FlatScene([], [mon]), arrs, max_trace_num=1, unit=unit, n_families=len(fam))
+    order = np.argsort(want["hit_root"], kind="stable")
+    assert mon.ndata == len(order) > 50
+    got_rays = [r for (_, _, _, r) in mon._data_raw]
+    assert [rays.index(r) for r in got_rays[:20]] == want["hit_root"][order][:20].tolist()
+    np.testing.assert_allclose(mon._P, np.stack([want["hit_px"], want["hit_py"], want["hit_pz"]], 1)[order], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(mon._t, want["hit_t"][order], rtol=1e-9)
+    mon.record([])
+    assert mon.ndata == len(order)

@@ -130,3 +130,44 @@ def test_own_classes_through_trace_table_equal_reference(name):
         if mw._data_raw:
             np.testing.assert_allclose(mg.get_yList(sort="YZ"), mw.get_yList(sort="YZ"), rtol=1e-9, atol=1e-12)
             np.testing.assert_allclose(mg.get_tYList(sort="YZ"), mw.get_tYList(sort="YZ"), rtol=1e-9, atol=1e-12)
+
+
+def test_monitor_record_explicit_segments_equals_reference():
+    """`Monitor.record(list_of_rays)` called directly (monitor.py:183-193): finite, infinite and dead segments,
+    misses, hits behind the origin; rows must reference the objects passed in."""
+    import optable_b200 as ob
+
+    ref = RH.load_reference()
+    rng = np.random.default_rng(7)
+
+    def build(mod):
+        mon = mod.Monitor(origin=[5, 0.2, -0.1], width=2, height=1.5).RotZ(0.3).RotY(-0.2)
+        rays = []
+        for k in range(40):
+            o = [rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1)]
+            d = [1.0, rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3)]
+            if k % 7 == 0:
+                d[0] = -1.0                                   # monitor behind the ray
+            kw = {}
+            if k % 3 == 0:
+                kw["length"] = float(rng.uniform(2.0, 9.0))   # may end before the plane
+            if k % 5 == 0:
+                kw["alive"] = False
+            if k % 2 == 0:
+                kw["w0"] = 0.01
+            rays.append(mod.Ray(o, d, wavelength=780e-7, intensity=float(rng.uniform(0.1, 1.0)), **kw))
+        return mon, rays
+
+    state = rng.bit_generator.state
+    mw, rw = build(ref)
+    rng.bit_generator.state = state
+    mg, rg = build(ob)
+    mw.record(rw)
+    mg.record(rg, engine=OracleEngine())
+    assert mg._updated and mg.ndata == len(mw._data_raw) > 5
+    for (Pw, Iw, tw, r_w), (Pg, Ig, tg, r_g) in zip(mw._data_raw, mg._data_raw):
+        assert np.linalg.norm(np.asarray(Pw) - Pg) <= 1e-9 and Iw == pytest.approx(Ig, rel=1e-12) and tw == pytest.approx(tg, rel=1e-9)
+        assert rw.index(r_w) == next(i for i, r in enumerate(rg) if r is r_g)
+    np.testing.assert_allclose(mg.get_yList(), mw.get_yList(), rtol=1e-9, atol=1e-12)
+    mg.record([], engine=OracleEngine())
+    assert mg.ndata == len(mw._data_raw)
