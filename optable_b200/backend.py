@@ -138,14 +138,20 @@ class Engine:
         return self._workspace
 
     def rays_to_device(self, arrs):
-        """dict of numpy arrays (flatten.pack_rays) -> dict of CUDA tensors."""
+        """dict of numpy arrays (flatten.pack_rays) -> dict of CUDA tensors (two transfers: the fp64 columns as
+        one block, flags + family as another)."""
         torch = self.torch
         dev = f"cuda:{self.device}"
-        out = {}
-        for k in A.RAY_F64:
-            out[k] = torch.from_numpy(np.ascontiguousarray(arrs[k], dtype=np.float64)).to(dev)
-        out["flags"] = torch.from_numpy(np.ascontiguousarray(arrs["flags"]).view(np.int32)).to(dev)
-        out["family"] = torch.from_numpy(np.ascontiguousarray(arrs["family"], dtype=np.int32)).to(dev)
+        n = len(arrs["ox"])
+        f = np.empty((len(A.RAY_F64), n), dtype=np.float64)
+        for j, k in enumerate(A.RAY_F64):
+            f[j] = arrs[k]
+        i = np.empty((2, n), dtype=np.int32)
+        i[0] = np.ascontiguousarray(arrs["flags"]).view(np.int32)
+        i[1] = arrs["family"]
+        fd, idev = torch.from_numpy(f).to(dev), torch.from_numpy(i).to(dev)
+        out = {k: fd[j] for j, k in enumerate(A.RAY_F64)}
+        out["flags"], out["family"] = idev[0], idev[1]
         return out
 
     @staticmethod
@@ -163,27 +169,48 @@ class Engine:
             setattr(s, k, None if v is None else v.data_ptr())
         return s
 
-    def alloc_result(self, scene: Scene, seg_capacity, hit_capacity, n_families, cap_counts=None):
+    SLAB_LIMIT = 4 << 20
+
+    def alloc_result(self, scene: Scene, seg_capacity, hit_capacity, n_families, cap_counts=None, slab=False):
+        """Device buffers for one trace + the optb_result that points at them. With `slab`, small results are
+        carved out of ONE zeroed buffer (returned as `result._slab`, layout in `result._layout`) so that the
+        whole result comes back with a single device-to-host copy."""
         torch = self.torch
         dev = f"cuda:{self.device}"
         dt = _result_fields(torch)
-        t = {}
-        for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32:
-            t[k] = torch.empty(int(seg_capacity), dtype=dt[k], device=dev)
-        for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64:
-            t[k] = torch.empty(int(hit_capacity), dtype=dt[k], device=dev)
         nm = max(scene.flat.n_monitors, 1)
-        t["hist_y"] = torch.zeros((nm, A.HIST_BINS), dtype=torch.int64, device=dev)
-        t["hist_yz"] = torch.zeros((nm, A.HIST_BINS, A.HIST_BINS), dtype=torch.int64, device=dev)
-        if cap_counts is None:
-            t["cap_counts"] = torch.zeros((max(scene.flat.n_capslots, 1), max(int(n_families), 1)), dtype=torch.int32, device=dev)
-        else:
-            t["cap_counts"] = torch.from_numpy(np.ascontiguousarray(cap_counts, dtype=np.int32)).to(dev)
-        t["counters"] = torch.zeros(A.C_COUNT, dtype=torch.int64, device=dev)
+        spec = [(k, dt[k], (int(seg_capacity),)) for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32]
+        spec += [(k, dt[k], (int(hit_capacity),)) for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64]
+        spec += [("hist_y", torch.int64, (nm, A.HIST_BINS)), ("hist_yz", torch.int64, (nm, A.HIST_BINS, A.HIST_BINS)),
+                 ("cap_counts", torch.int32, (max(scene.flat.n_capslots, 1), max(int(n_families), 1))),
+                 ("counters", torch.int64, (A.C_COUNT,))]
+        size = {torch.float64: 8, torch.int64: 8, torch.int32: 4}
+        layout, total = {}, 0
+        for k, d, shape in spec:
+            nbytes = size[d] * int(np.prod(shape))
+            layout[k] = (total, nbytes, d, shape)
+            total += (nbytes + 15) & ~15
+        t = {}
         r = A.Result()
+        if slab and total <= self.SLAB_LIMIT:
+            buf = torch.zeros(total, dtype=torch.uint8, device=dev)
+            base = buf.data_ptr()
+            for k, (off, nbytes, d, shape) in layout.items():
+                setattr(r, k, base + off)
+            off, nbytes, d, shape = layout["cap_counts"]
+            t["cap_counts"] = buf[off:off + nbytes].view(d).view(shape)
+            r._slab, r._layout = buf, layout
+        else:
+            for k, d, shape in spec:
+                zero = k in ("hist_y", "hist_yz", "cap_counts", "counters")
+                t[k] = (torch.zeros if zero else torch.empty)(shape, dtype=d, device=dev)
+            r._slab = None
+        if cap_counts is not None:
+            t["cap_counts"].copy_(torch.from_numpy(np.ascontiguousarray(cap_counts, dtype=np.int32)))
         r.seg_capacity, r.hit_capacity = int(seg_capacity), int(hit_capacity)
-        for k, v in t.items():
-            setattr(r, k, v.data_ptr())
+        if r._slab is None:
+            for k, v in t.items():
+                setattr(r, k, v.data_ptr())
         return r, t
 
     @staticmethod
@@ -233,20 +260,40 @@ class Engine:
             fam_size = np.bincount(arrs["family"], minlength=n_families).max() if n else 0
             capmax = flat.node_f[flat.node_i[:, A.NI_CAPSLOT] >= 0, A.NF_CAPMAX].min()
             slack = int(caps0.max() + int(max_trace_num) * int(fam_size) <= capmax)
-        # pass 1: count rows (interact-count side effects go to a scratch table)
-        prm = self.make_params(max_trace_num, unit, False, False, False, chain_len, n_families, slack)
-        res, t = self.alloc_result(scene, 0, 0, n_families, caps0)
-        self.trace_device(scene, rays_t, prm, res, max_live)
-        cnt = t["counters"].cpu().numpy()
+        # Row counts are only known after the trace. First try with capacities guessed from the batch; the
+        # counters keep counting past the capacity, so an overflowing attempt is repeated once with exact sizes
+        # (interact counts restart from caps0: every attempt gets a fresh table).
+        pops_max = n * int(max_trace_num)
+        nseg = min(pops_max, 8 * n + 1024) if record_segments else 0
+        nhit = min(pops_max * flat.n_monitors, 8 * n + 1024) if record_hits else 0
+        prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families, slack)
+        np_dt = {torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32}
+        for attempt in range(2):
+            res, t = self.alloc_result(scene, nseg, nhit, n_families, caps0, slab=True)
+            self.trace_device(scene, rays_t, prm, res, max_live)
+            host = None
+            if res._slab is not None:  # everything in one copy (synchronises)
+                raw = res._slab.cpu().numpy()
+                host = {k: raw[off:off + nb].view(np_dt[d]).reshape(shape) for k, (off, nb, d, shape) in res._layout.items()}
+                cnt = host["counters"]
+            else:
+                cnt = t["counters"].cpu().numpy()
+            st = int(cnt[A.C_STATUS])
+            if not st & (A.ST_SEG_OVERFLOW | A.ST_HIT_OVERFLOW):
+                break
+            if st & A.ST_WORK_OVERFLOW:
+                self._raise_status(cnt)
+            nseg = int(cnt[A.C_SEGMENTS]) if record_segments else 0
+            nhit = int(cnt[A.C_HITS]) if record_hits else 0
         self._raise_status(cnt)
         nseg = int(cnt[A.C_SEGMENTS]) if record_segments else 0
         nhit = int(cnt[A.C_HITS]) if record_hits else 0
-        # pass 2: record
-        prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families, slack)
-        res, t = self.alloc_result(scene, nseg, nhit, n_families, caps0)
-        self.trace_device(scene, rays_t, prm, res, max_live)
-        torch.cuda.synchronize(self.device)
-        out = {k: v.cpu().numpy() for k, v in t.items()}
+        trim = {k: nseg for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32}
+        trim.update({k: nhit for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64})
+        if host is not None:
+            out = {k: (v[:trim[k]] if k in trim else v) for k, v in host.items()}
+        else:
+            out = {k: (v[:trim[k]] if k in trim else v).cpu().numpy() for k, v in t.items()}
         for k in A.SEG_U32 + A.HIT_U32:
             out[k] = out[k].view(np.uint32)
         self._raise_status(out["counters"])

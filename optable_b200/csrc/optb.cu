@@ -647,10 +647,13 @@ struct optb_ctx {
   unsigned int* h_hdr;             // pinned
   cudaStream_t s_h2d, s_run, s_d2h;  // pipelined optb_trace_host
   unsigned long long* h_chunk; size_t h_chunk_n;  // pinned per-chunk counters
+  // Retired scene blobs, kept for the next upload: cudaMalloc/cudaFree cost milliseconds each (and cudaFree
+  // synchronises the device), which is most of the latency of a small trace that re-uploads its scene per call.
+  struct { unsigned char* p; size_t cap; } pool[8];
 };
 
 struct optb_scene {
-  unsigned char* d_blob; uint32_t blob_bytes; SceneOff off;
+  unsigned char* d_blob; size_t blob_cap; uint32_t blob_bytes; SceneOff off;
   int n_nodes, n_leaves, n_mats, n_mons, n_caps; long long n_aux;
   int max_children; int has_boxes; int has_asph;
   bool in_smem; bool hist_smem; uint32_t smem_bytes;
@@ -691,6 +694,7 @@ extern "C" int optb_ctx_destroy(optb_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   if (ctx->arena) cudaFree(ctx->arena);
+  for (auto& b : ctx->pool) if (b.p) cudaFree(b.p);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->h_hdr) cudaFreeHost(ctx->h_hdr);
   if (ctx->h_chunk) cudaFreeHost(ctx->h_chunk);
@@ -794,8 +798,18 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   size_t used = s->in_smem ? o : 0;
   s->hist_smem = (hist_bytes > 0 && used + hist_bytes <= std::min<size_t>(budget, used + 65536));
   s->smem_bytes = (uint32_t)(used + (s->hist_smem ? hist_bytes : 0));
-  cudaError_t e = cudaMalloc((void**)&s->d_blob, o);
-  if (e != cudaSuccess) { delete s; return fail(ctx, -10, "cudaMalloc(scene)", e); }
+  cudaError_t e = cudaSuccess;
+  int pick = -1;  // smallest retired blob that is large enough
+  for (int k = 0; k < 8; k++)
+    if (ctx->pool[k].p && ctx->pool[k].cap >= o && (pick < 0 || ctx->pool[k].cap < ctx->pool[pick].cap)) pick = k;
+  if (pick >= 0) {
+    s->d_blob = ctx->pool[pick].p; s->blob_cap = ctx->pool[pick].cap;
+    ctx->pool[pick].p = nullptr; ctx->pool[pick].cap = 0;
+  } else {
+    s->blob_cap = (o + 65535) & ~(size_t)65535;
+    e = cudaMalloc((void**)&s->d_blob, s->blob_cap);
+    if (e != cudaSuccess) { delete s; return fail(ctx, -10, "cudaMalloc(scene)", e); }
+  }
   e = cudaMemcpy(s->d_blob, host.data(), o, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(s->d_blob); delete s; return fail(ctx, -10, "cudaMemcpy(scene)", e); }
   *out = s;
@@ -805,7 +819,17 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
 extern "C" int optb_scene_destroy(optb_ctx* ctx, optb_scene* s) {
   if (!s) return 0;
   if (ctx) cudaSetDevice(ctx->device);
-  if (s->d_blob) cudaFree(s->d_blob);
+  if (s->d_blob) {
+    int slot = -1;
+    if (ctx && s->blob_cap <= ((size_t)64 << 20))
+      for (int k = 0; k < 8 && slot < 0; k++) if (!ctx->pool[k].p) slot = k;
+    if (slot >= 0) {
+      cudaDeviceSynchronize();  // what cudaFree would have done: no kernel may still be reading the blob
+      ctx->pool[slot].p = s->d_blob; ctx->pool[slot].cap = s->blob_cap;
+    } else {
+      cudaFree(s->d_blob);
+    }
+  }
   delete s;
   return 0;
 }
