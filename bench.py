@@ -115,7 +115,27 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
 
+    def _nvml_loop(self):
+        """NVML in-process: a sample every 10 ms (the nvidia-smi binary needs ~0.3 s per query, i.e. one sample
+        for a 0.3 s timed region)."""
+        import pynvml as N
+
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (0x8, 0x40, 0x20, 0x4)  # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        while not self._halt.is_set():
+            sm, mask = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), int(reasons_fn(h))
+            self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for b in bits])
+            self._halt.wait(0.01)
+
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            pass
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
