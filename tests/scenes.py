@@ -356,6 +356,70 @@ def caps_binding(ns):
     return Scene([ps], rays, [ns.Monitor([-3, 0, 0], width=2 * L, height=2 * L)], limit={"max_trace_num": 80})
 
 
+def fuzz(ns, seed, n_rays=24):
+    """Random scene for the fuzz parity tests: 4-9 components drawn from the whole component zoo with random
+    parameters, positions in a 15 x 5 x 1.6 box, mostly facing the beam, 2 monitors, a cone of rays from the
+    left (3 wavelengths, some without q, some length-limited). Deterministic in `seed`; both packages build the
+    same scene because all randomness is drawn here."""
+    rng = np.random.default_rng(SEED * 7 + seed)
+    U = rng.uniform
+
+    def place(c):
+        # mostly facing the beam (within +-70 degrees), one in five at an arbitrary azimuth
+        az = U(-np.pi, np.pi) if U() < 0.2 else U(-1.2, 1.2)
+        return c.RotZ(az).RotY(U(-0.4, 0.4)).RotX(U(-0.3, 0.3))
+
+    def pos():
+        return [U(3, 18), U(-2.5, 2.5), U(-0.8, 0.8)]
+
+    glass = [lambda: 1.0 + U(0.3, 0.9), lambda: ns.Glass_NBK7(), lambda: ns.Glass_NSF5() if hasattr(ns, "Glass_NSF5") else 1.6]
+    palette = [
+        lambda: ns.Mirror(pos(), radius=U(0.5, 2.5), reflectivity=U(0.3, 1.0), transmission=U(0.0, 0.5)),
+        lambda: ns.SquareMirror(pos(), width=U(1, 4), height=U(1, 4), reflectivity=U(0.5, 1.0)),
+        lambda: ns.BeamSplitter(pos(), width=U(1, 4), height=U(1, 4), eta=U(0.2, 0.8)),
+        lambda: ns.CylMirror(pos(), radius=U(1.0, 3.0), height=U(2, 4), theta_range=(-U(0.5, 3.1), U(0.5, 3.1))),
+        lambda: ns.Lens(pos(), focal_length=U(-8, 8) or 5.0, radius=U(0.8, 2.5), transmission=U(0.7, 1.0)),
+        lambda: ns.Block(pos(), hole=ns.Circle(U(0.2, 0.8)), width=U(2, 4), height=U(2, 4)),
+        lambda: ns.GlassSlab(pos(), width=U(2, 4), height=U(2, 4), thickness=U(0.2, 1.5), n1=1.0, n2=rng.choice(glass)(),
+                             reflectivity=U(0.0, 0.2)),
+        lambda: ns.CircleGlassSlab(pos(), radius=U(0.8, 2.0), thickness=U(0.2, 1.0), n1=1.0, n2=1.0 + U(0.3, 0.8),
+                                   reflectivity2=U(0.0, 0.1)),
+        lambda: ns.WedgePlate(pos(), width=U(2, 4), height=U(2, 4), thickness=U(0.3, 0.8), wedge_angle=U(0.0, 0.1), n1=1.0,
+                              n2=1.0 + U(0.3, 0.7)),
+        lambda: ns.PlanoConvexLens(pos(), EFL=U(6, 20), CT=U(0.4, 0.8), diameter=U(1.5, 3.0), R=U(4, 10)),
+        lambda: ns.BiConvexLens(pos(), CT=U(0.5, 0.9), R1=U(8, 20), R2=-U(8, 20), diameter=U(1.5, 3.0), n=1.0 + U(0.4, 0.8)),
+        lambda: ns.Doublet(pos(), CT1=U(0.8, 1.4), CT2=U(0.4, 0.8), R1=U(14, 22), R2=-U(10, 16), R3=-U(30, 50),
+                           diameter=U(4, 7), n12=ns.Glass_NBK7(), n23=1.0 + U(0.5, 0.8)),
+        lambda: ns.Prism(pos(), width=U(1.5, 3), height=U(1.5, 3), n1=1.0, n2=1.0 + U(0.4, 0.7), reflectivity_hyp=U(0.0, 0.2)),
+        lambda: ns.MirrorCube(pos(), L=U(1.0, 2.5)),
+        lambda: ns.MLA(pos(), N=(int(rng.integers(2, 5)), int(rng.integers(2, 4))), pitch=U(0.4, 0.8), focal_length=U(2, 6),
+                       radius=U(0.15, 0.35)),
+        lambda: ns.DMD(pos(), N=(int(rng.integers(2, 4)), int(rng.integers(2, 4))), pitch=U(0.4, 0.8), tilt_angle=U(0.5, 1.0)),
+        lambda: ns.ASphericParametricLens(pos(), CT=U(0.5, 0.9), diameter=U(2.0, 3.5), n=1.0 + U(0.4, 0.7), R=U(4, 9),
+                                          kappa=-U(0.2, 1.2), a4=U(-2e-4, 2e-4), a6=U(-5e-6, 5e-6)),
+        lambda: ns.SphereRefractive(pos(), radius=U(2.0, 6.0), height=U(0.5, 1.5), n1=1.0, n2=1.0 + U(0.3, 0.8),
+                                    reflectivity=U(0.0, 0.15)),
+    ]
+    comps = []
+    for k in rng.choice(len(palette), size=int(rng.integers(4, 10))):
+        c = place(palette[int(k)]())
+        if U() < 0.15:
+            c.max_interact_count = None  # (exercise the attribute without binding caps: family-serial has its own tests)
+        comps.append(c)
+    wls = (450e-7, 633e-7, 1064e-7)
+    rays = []
+    for k in range(n_rays):
+        kw = {"wavelength": wls[k % 3]}
+        if k % 4:
+            kw["w0"] = U(20e-4, 80e-4)
+        if k % 11 == 5:
+            kw["length"] = U(4, 40)
+        d = [1.0, 0.12 * rng.standard_normal(), 0.04 * rng.standard_normal()]
+        rays.append(ns.Ray([U(-1, 1), U(-1.5, 1.5), U(-0.5, 0.5)], d, intensity=U(0.2, 1.0), **kw))
+    mons = [place(ns.Monitor(pos(), U(4, 12), U(4, 12))), ns.Monitor([20, 0, 0], 30, 12)]
+    return Scene(comps, rays, mons, limit={"max_trace_num": 60})
+
+
 REGISTRY = {
     "gaussian_beam": gaussian_beam,
     "glass_slab": glass_slab,
@@ -375,6 +439,9 @@ REGISTRY = {
     "extras": extras,
     "ripa": lambda ns: ripa(ns, n_rays=3, limit=150),
 }
+# a dozen random scenes are ordinary fixtures too (reference-generated goldens); the fuzz tests add hundreds more
+for _seed in range(12):
+    REGISTRY[f"fuzz_{_seed:02d}"] = (lambda ns, _s=_seed: fuzz(ns, _s))
 
 
 # ---- array-level ray batches for the scale tests (no Python Ray objects) ---------------------------------------

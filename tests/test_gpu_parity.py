@@ -14,13 +14,7 @@ def engine():
     return Engine.get(0)
 
 
-def _q_rtol(flat):
-    """Gaussian q after an ASphere whose radius of curvature comes from the reference's finite-difference
-    second derivative (surfaces.py:355-369, h = 1e-4 radius) is ill-conditioned: one ulp of f_asphere moves
-    ROC by ~5e-9 relative. Every other field keeps the 1e-9 bar."""
-    from optable_b200 import _abi as A
-
-    return 1e-6 if (flat.node_i[:, A.NI_ROCKIND] == A.ROC_ASPHERE_FD).any() else parity.RTOL
+_q_rtol = parity.q_rtol_for
 
 
 def _gpu(engine, flat, rays, params, **kw):
@@ -48,3 +42,26 @@ def test_wavefront_scheduling_does_not_change_results(engine, name, chain_len):
     flat, rays, params, ref = golden_io.load(name)
     _, got = _gpu(engine, flat, rays, params, chain_len=chain_len)
     parity.compare(ref, got, q_rtol=_q_rtol(flat), label=f"{name}/chain{chain_len}")
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_fuzz_scenes_cuda_equals_oracle(engine, block):
+    """300 random scenes over the whole component zoo (tests/scenes.fuzz, 64 rays each, built with this package's
+    classes), CUDA path through the C ABI against the C oracle: indices and pop counts exact, fields to 1e-9."""
+    import optable_b200 as ob
+    from optable_b200.flatten import FlatScene, pack_rays, trace_cap
+    from oracle import oracle as O
+    from oracle import ref_harness as RH
+    from tests import scenes
+
+    pops = 0
+    for seed in range(1000 + 50 * block, 1050 + 50 * block):
+        sc = scenes.fuzz(ob, seed, n_rays=64)
+        flat = FlatScene(sc.components, sc.monitors)
+        arrs, fam_ids, unit = pack_rays(sc.rays)
+        params = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
+        want = RH.arrays_from_result(O.trace(flat, arrs, **params))
+        _, got = _gpu(engine, flat, arrs, params)
+        parity.compare(want, got, q_rtol=_q_rtol(flat), label=f"fuzz seed {seed}")
+        pops += len(want["seg_root"])
+    assert pops > 5000
