@@ -44,24 +44,48 @@ def test_wavefront_scheduling_does_not_change_results(engine, name, chain_len):
     parity.compare(ref, got, q_rtol=_q_rtol(flat), label=f"{name}/chain{chain_len}")
 
 
+FUZZ_PATH_RTOL = 1e-6
+
+
 @pytest.mark.parametrize("block", range(6))
 def test_fuzz_scenes_cuda_equals_oracle(engine, block):
     """300 random scenes over the whole component zoo (tests/scenes.fuzz, 64 rays each, built with this package's
-    classes), CUDA path through the C ABI against the C oracle: indices and pop counts exact, fields to 1e-9."""
+    classes), CUDA path through the C ABI against the C oracle.
+    (a) Whole paths (up to 60 pops, splitting): winning leaf, pop numbering and segment counts exact (equal-distance
+        ties flagged, see parity.compare_flagging_ties); fields to 1e-6 (q 1e-5), because random scenes trap rays between
+        curved faces where the reference's own root tolerance (brentq xtol = 2e-12 absolute) is amplified per bounce.
+    (b) Single interactions: every popped ray of (a) restarted on both sides from identical inputs and traced for
+        three pops: the strict 1e-9 bar on every field."""
     import optable_b200 as ob
     from optable_b200.flatten import FlatScene, pack_rays, trace_cap
     from oracle import oracle as O
     from oracle import ref_harness as RH
     from tests import scenes
 
-    pops = 0
+    pops = flagged = rays = restarted = 0
     for seed in range(1000 + 50 * block, 1050 + 50 * block):
         sc = scenes.fuzz(ob, seed, n_rays=64)
         flat = FlatScene(sc.components, sc.monitors)
         arrs, fam_ids, unit = pack_rays(sc.rays)
         params = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
-        want = RH.arrays_from_result(O.trace(flat, arrs, **params))
+        raw = O.trace(flat, arrs, **params)
+        want = RH.arrays_from_result(raw)
         _, got = _gpu(engine, flat, arrs, params)
-        parity.compare(want, got, q_rtol=_q_rtol(flat), label=f"fuzz seed {seed}")
+        _, ties = parity.compare_flagging_ties(flat, want, got, rtol=FUZZ_PATH_RTOL, q_rtol=10 * max(_q_rtol(flat), FUZZ_PATH_RTOL),
+                                               label=f"fuzz seed {seed}")
         pops += len(want["seg_root"])
-    assert pops > 5000
+        flagged += len(ties)
+        rays += len(sc.rays)
+        batch = parity.restart_batch(raw, np.nonzero(np.isinf(arrs["length"]))[0])
+        p1 = dict(max_trace_num=3, unit=unit, n_families=len(batch["ox"]))
+        want1 = RH.arrays_from_result(O.trace(flat, batch, **p1))
+        _, got1 = _gpu(engine, flat, batch, p1)
+        # (q behind a finite-difference asphere curvature: the 1e-6 carve-out of the fixtures grows to 1e-5 once
+        # random upstream optics have made |q| hundreds of times the radius of curvature)
+        q1 = 1e-5 if _q_rtol(flat) > parity.RTOL else parity.RTOL
+        _, ties1 = parity.compare_flagging_ties(flat, want1, got1, q_rtol=q1, label=f"fuzz seed {seed} (restarted)")
+        restarted += len(batch["ox"])
+        flagged += len(ties1)
+        rays += len(batch["ox"])
+    # equal-distance ties between coplanar overlapping apertures: a few per 1e4 rays
+    assert pops > 5000 and restarted > 4000 and flagged <= 2e-3 * rays, (flagged, rays)
