@@ -292,11 +292,17 @@ class Engine:
         trim.update({k: nhit for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64})
         if host is not None:
             out = {k: (v[:trim[k]] if k in trim else v) for k, v in host.items()}
+            presorted = False
         else:
-            out = {k: (v[:trim[k]] if k in trim else v).cpu().numpy() for k, v in t.items()}
+            # large results: put the rows into reference order on the device (one 64-bit key per row), then copy
+            dev_t = {k: (v[:trim[k]] if k in trim else v) for k, v in t.items()}
+            presorted = self._sort_rows_on_device(dev_t, nseg, nhit, int(max_trace_num), flat.n_monitors)
+            out = {k: v.cpu().numpy() for k, v in dev_t.items()}
         for k in A.SEG_U32 + A.HIT_U32:
             out[k] = out[k].view(np.uint32)
         self._raise_status(out["counters"])
+        if presorted:
+            return out
         if record_segments and nseg:
             order = np.lexsort((out["seg_pop"], out["seg_root"]))
             for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32:
@@ -306,6 +312,28 @@ class Engine:
             for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64:
                 out[k] = out[k][order]
         return out
+
+    def _sort_rows_on_device(self, t, nseg, nhit, max_trace_num, n_monitors):
+        """Reorder the row columns in `t` (CUDA tensors) to (root, pop) / (root, monitor, pop). The key is packed
+        into one int64 (root < 2^32, pop < max_trace_num); returns False when it would not fit (caller sorts on
+        the host)."""
+        torch = self.torch
+        pop_bits = max(int(max_trace_num), 1).bit_length()
+        mon_bits = max(int(n_monitors), 1).bit_length()
+        if 32 + pop_bits + mon_bits > 63:
+            return False
+        u32 = lambda x: x.to(torch.int64) & 0xFFFFFFFF
+        if nseg:
+            key = (u32(t["seg_root"]) << pop_bits) | u32(t["seg_pop"])
+            order = torch.argsort(key)
+            for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32:
+                t[k] = t[k][order]
+        if nhit:
+            key = (((u32(t["hit_root"]) << mon_bits) | t["hit_monitor"].to(torch.int64)) << pop_bits) | u32(t["hit_pop"])
+            order = torch.argsort(key)
+            for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64:
+                t[k] = t[k][order]
+        return True
 
     @staticmethod
     def _raise_status(counters):
