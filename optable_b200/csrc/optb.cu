@@ -312,7 +312,11 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
 }
 
 template <bool SMEM, bool SERIAL, bool BOXES, bool ASPH>
-__global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceArgs a) {
+// Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
+// spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
+// whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
+__global__ void __launch_bounds__(kBlock, (SMEM || ASPH || SERIAL) ? OPTB_MIN_BLOCKS : OPTB_MIN_BLOCKS + 1)
+trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   // The closest-hit search only needs a ray's geometry. Its radiometric state (intensity, wavelength, q, path
