@@ -111,15 +111,17 @@ struct BoxRay {
 // a well-formed box, bmin <= bmax).
 OPTB_DEV bool slab_hit(const BoxRay& r, const double* __restrict__ bb) {
   if (!r.any_par) {
-    double t1 = 0.0, t2 = INFINITY;
+    double tn[3], tf[3];
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
-      double tn = (bb[2 * ax + r.near[ax]] - r.o[ax]) * r.inv[ax];
-      double tf = (bb[2 * ax + 1 - r.near[ax]] - r.o[ax]) * r.inv[ax];
-      t1 = dmax(t1, tn);
-      t2 = dmin(t2, tf);
+      tn[ax] = (bb[2 * ax + r.near[ax]] - r.o[ax]) * r.inv[ax];
+      tf[ax] = (bb[2 * ax + 1 - r.near[ax]] - r.o[ax]) * r.inv[ax];
     }
-    return (t2 + 1e-12 >= t1) && (t2 >= 0.0);
+    // t2 + 1e-12 >= max(0, tn0, tn1, tn2) and t2 >= 0, without forming the maximum: one compare per candidate
+    // (a double max is a compare plus two selects); the comparison against 0 is implied by t2 >= 0.
+    const double t2 = dmin(dmin(tf[0], tf[1]), tf[2]);
+    const double e = t2 + 1e-12;
+    return (t2 >= 0.0) && (e >= tn[0]) && (e >= tn[1]) && (e >= tn[2]);
   }
   double t1 = 0.0, t2 = INFINITY;
 #pragma unroll
