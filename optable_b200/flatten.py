@@ -113,6 +113,9 @@ def _csg_spec(surface):
     return op, cm["self"], cm["other"]
 
 
+_BVH_PLANS = {}  # (fanout, n, box bytes) -> hierarchy plan, see FlatScene._wrap_runs
+
+
 class FlatScene:
     """Numpy tables + bookkeeping for one OpticalTable."""
 
@@ -199,6 +202,12 @@ class FlatScene:
         row), at most BVH_FANOUT runs per node."""
         boxes = np.array([c[1][A.NF_AABB:A.NF_AABB + 6] for c in children], dtype=np.float64)
         F = max(2, self.BVH_FANOUT)
+        # the hierarchy is a pure function of the children's boxes: keep it across calls (a GUI loop or a parameter
+        # sweep re-flattens the same arrays many times); plan = nested (box, members) tuples over child indices
+        key = (F, boxes.shape[0], boxes.tobytes())
+        plan = _BVH_PLANS.get(key)
+        if plan is not None:
+            return self._from_plan(plan, children)
 
         def area(lo, hi):
             d = np.maximum(hi - lo, 0.0)
@@ -232,7 +241,29 @@ class FlatScene:
                 out.append(children[pa] if pb - pa == 1 else self._synthetic(build(pa, pb)))
             return out
 
-        return build(0, len(children))
+        built = build(0, len(children))
+        index = {id(c): k for k, c in enumerate(children)}
+
+        def to_plan(tree):
+            k = index.get(id(tree))
+            return k if k is not None else (tuple(tree[1][A.NF_AABB:A.NF_AABB + 6]), tuple(to_plan(m) for m in tree[2]))
+
+        if len(_BVH_PLANS) >= 64:
+            _BVH_PLANS.clear()
+        _BVH_PLANS[key] = tuple(to_plan(t) for t in built)
+        return built
+
+    def _from_plan(self, plan, children):
+        out = []
+        for item in plan:
+            if isinstance(item, int):
+                out.append(children[item])
+            else:
+                ni, nf = self._blank()
+                ni[A.NI_GEOM], ni[A.NI_AABB] = A.G_GROUP, 1
+                nf[A.NF_AABB:A.NF_AABB + 6] = item[0]
+                out.append((ni, nf, self._from_plan(item[1], children)))
+        return out
 
     def _visit(self, comp, in_group):
         """Component (sub)tree -> (node_i row, node_f row, children) or None when nothing can be hit."""
