@@ -15,6 +15,7 @@ from .assemblies import (ComponentGroup, GlassSlab, CircleGlassSlab, MLA, MMA, M
                          MirrorPair, Prism, TriangularPrism, MirrorPrism, MirrorCube, DovePrism, PlanoConvexLens,
                          BiConvexLens, Doublet, ASphericLens, ASphericExactSphericalLens, ASphericParametricLens)
 from .monitors import Monitor
+from .solvers import solve_ray_bboxes_intersections, solve_ray_ray_intersection, solve_normal_to_normal_rotation
 from .table import OpticalTable, install, trace_table
 
 __all__ = [n for n in dir() if not n.startswith("_")]
