@@ -72,9 +72,26 @@ def make_abcd():
     return np.asarray(Ms)
 
 
+def make_ripa2_post():
+    """Fixture for the analysis of examples/ripa_gen2_2nd_simplified.py:169-203 (Monitor.get_rays / get_ray_id by
+    ray id, solve_ray_ray_intersection, Gaussian-beam helpers on the recorded segments), run by the reference."""
+    ref = RH.load_reference()
+    sc = scenes.ripa2_simplified(ref)
+    table = ref.OpticalTable()
+    table.add_components(sc.components)
+    table.add_monitors(sc.monitors)
+    table.ray_tracing(sc.rays)
+    post = scenes.ripa2_postprocess(ref, table, sc)
+    np.savez_compressed(os.path.join(OUT, "ripa2_post.npz"), **post)
+    return post
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["abcd"]:
         print(make_abcd()[:2])
+        sys.exit(0)
+    if sys.argv[1:] == ["ripa2_post"]:
+        print({k: v.shape for k, v in make_ripa2_post().items()})
         sys.exit(0)
     for name in (sys.argv[1:] or scenes.REGISTRY):
         nseg, nhit = make(name)

@@ -356,6 +356,58 @@ def caps_binding(ns):
     return Scene([ps], rays, [ns.Monitor([-3, 0, 0], width=2 * L, height=2 * L)], limit={"max_trace_num": 80})
 
 
+def ripa2_simplified(ns, spacing=10):
+    """examples/ripa_gen2_2nd_simplified.py:26-131: two tilted fans of Gaussian rays with explicit ids (reverse ray
+    tracing) through a 4f pair of parametric aspheres (Sellmeier UVFS), everything held by one ComponentGroup
+    (add_rays / add_components / add_monitors, TY translations, Propagate, _RotAroundLocal)."""
+    BW = 6.834682
+    wl, DMLA, NMLA = 780e-7, 420e-4, 80
+    L = DMLA * NMLA / 2
+    d = 3e8 / (2 * BW * 1e9) / 0.01
+    w0 = np.sqrt(wl * (2 * d) / (2 * np.pi))
+    theta0 = np.arctan(DMLA / d / 2)
+    kappa, a4, a6 = -1.01705, -4.00e-11, 3.180e-15
+
+    def fan(idxs, sign, offset=0):
+        return [ns.Ray([0, L - (i + offset) * DMLA, 0.0], [1, 0, 0], wavelength=wl, w0=w0, id=int(k + NMLA * int(sign == -1)))
+                .Propagate(0.0)._RotAroundLocal([0, 0, 1], [0, 0, 0], -sign * theta0) for k, i in enumerate(idxs)]
+
+    rays = fan(range(0, NMLA, spacing), 1) + fan(range(0, NMLA, spacing), -1, offset=1)
+    EFL, CT = 43.17, 0.8
+    glass = ns.Glass_UVFS()
+    R = EFL * (glass.n(780e-9) - 1)
+    lens = dict(CT=CT, diameter=2.54 * 3, R=R, n=glass, kappa=kappa, a4=a4 * (1e-2 / 1e-3) ** 4, a6=a6 * (1e-2 / 1e-3) ** 6)
+    l0 = ns.ASphericParametricLens([EFL, 0, 0], name="L0", **lens).TY(DMLA / 2)
+    l1 = ns.ASphericParametricLens([3 * EFL, 0, 0], name="L1", **lens).RotZ(np.pi).TY(DMLA / 2)
+    mons = [ns.Monitor([-0.5, -2.5, 0], width=5, height=5, name="R2 Monitor 0").TY(L),
+            ns.Monitor([4 * EFL, 0, 0], width=5, height=5, name="R2 Monitor 1"),
+            ns.Monitor([4 * EFL + d, 0, 0], width=5, height=5, name="R2 Monitor 2")]
+    group = ns.ComponentGroup([0, 0, 0], name="RIPA2")
+    group.add_rays(rays)
+    group.add_components([l0, l1])
+    group.add_monitors(mons)
+    return Scene([group], group.rays, group.monitors)
+
+
+def ripa2_postprocess(ns, table, scene):
+    """The analysis part of examples/ripa_gen2_2nd_simplified.py:169-203 on a traced table: pair every ray of the
+    first fan with its partner (id + 80) at the last monitor, intersect the pair, and derive the mirror position,
+    normal, radius of curvature and mean optical path length at the crossing. Returns arrays (one row per pair)."""
+    mon2 = scene.monitors[2]
+    d = 3e8 / (2 * 6.834682 * 1e9) / 0.01
+    first = [r for r in mon2.get_rays(sort="ID") if r._id < 80]
+    P, nrm, roc, pl = [], [], [], []
+    for ray0 in first:
+        ray1, _ = mon2.get_ray_id(ray0._id + 80)
+        t0, t1, Pk, nk = ns.solve_ray_ray_intersection(ray0.origin, ray0.direction, ray1.origin, ray1.direction)
+        d0, d1 = ray0.distance_to_waist(ray0.q_at_z(t0)), ray1.distance_to_waist(ray1.q_at_z(t1))
+        P.append(Pk)
+        nrm.append(nk)
+        roc.append(2 * (d ** 2 + d0 * d1) / (d0 + d1))
+        pl.append((ray0.pathlength(t0) + ray1.pathlength(t1)) / 2)
+    return {"P": np.array(P), "n": np.array(nrm), "roc": np.array(roc), "pathlength": np.array(pl)}
+
+
 def fuzz(ns, seed, n_rays=24):
     """Random scene for the fuzz parity tests: 4-9 components drawn from the whole component zoo with random
     parameters, positions in a 15 x 5 x 1.6 box, mostly facing the beam, 2 monitors, a cone of rays from the
@@ -438,6 +490,7 @@ REGISTRY = {
     "caps_binding": caps_binding,
     "extras": extras,
     "ripa": lambda ns: ripa(ns, n_rays=3, limit=150),
+    "ripa2_simplified": ripa2_simplified,
 }
 # a dozen random scenes are ordinary fixtures too (reference-generated goldens); the fuzz tests add hundreds more
 for _seed in range(12):

@@ -169,3 +169,23 @@ def test_monitor_record_explicit_segments():
     np.testing.assert_allclose(mon._t, want["hit_t"][order], rtol=1e-9)
     mon.record([])
     assert mon.ndata == len(order)
+
+
+def test_ripa2_example_with_its_analysis():
+    """examples/ripa_gen2_2nd_simplified.py end to end on the new back end: scene held by a ComponentGroup, trace,
+    then the script's own analysis (monitor rows looked up by ray id, ray-ray intersections, beam helpers) against
+    what the reference computes for it (tests/golden/ripa2_post.npz)."""
+    import os
+
+    sc = scenes.ripa2_simplified(ob)
+    table = ob.OpticalTable()
+    table.add_components(sc.components)
+    table.add_monitors(sc.monitors)
+    table.ray_tracing(sc.rays)
+    got = scenes.ripa2_postprocess(ob, table, sc)
+    want = np.load(os.path.join(golden_io.GOLDEN_DIR, "ripa2_post.npz"))
+    assert got["P"].shape == want["P"].shape == (8, 3)
+    np.testing.assert_allclose(got["P"], want["P"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(got["n"], want["n"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got["pathlength"], want["pathlength"], rtol=1e-9)
+    np.testing.assert_allclose(got["roc"], want["roc"], rtol=1e-5)   # q behind finite-difference asphere curvatures

@@ -171,3 +171,24 @@ def test_monitor_record_explicit_segments_equals_reference():
     np.testing.assert_allclose(mg.get_yList(), mw.get_yList(), rtol=1e-9, atol=1e-12)
     mg.record([], engine=OracleEngine())
     assert mg.ndata == len(mw._data_raw)
+
+
+def test_ripa2_example_analysis_with_oracle_engine():
+    """Host side of the same example (tests/test_gpu_api.py::test_ripa2_example_with_its_analysis) on the CPU."""
+    import os
+
+    import optable_b200 as ob
+    from optable_b200.table import trace_table
+    from tests import golden_io
+
+    sc = scenes.ripa2_simplified(ob)
+    table = ob.OpticalTable()
+    table.add_components(sc.components)
+    table.add_monitors(sc.monitors)
+    table.rays.extend(trace_table(table, list(sc.rays), None, engine=OracleEngine()))
+    got = scenes.ripa2_postprocess(ob, table, sc)
+    want = np.load(os.path.join(golden_io.GOLDEN_DIR, "ripa2_post.npz"))
+    np.testing.assert_allclose(got["P"], want["P"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(got["n"], want["n"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got["pathlength"], want["pathlength"], rtol=1e-9)
+    np.testing.assert_allclose(got["roc"], want["roc"], rtol=1e-5)
