@@ -43,8 +43,10 @@ struct RayBuf {
 
 struct Header {  // first bytes of the workspace
   unsigned int work_ctr;
-  unsigned int n_next;
-  unsigned int pad[14];
+  unsigned int n_next;      // size of the wavefront the last compaction produced
+  unsigned int n_prev;      // size of the wavefront that compaction consumed (for generations launched unseen)
+  unsigned int empty_gens;  // generations launched unseen that found nothing to do
+  unsigned int pad[12];
 };
 
 struct SceneOff { uint32_t trav, nf, ni, matk, matf, mon, aux; };
@@ -500,8 +502,9 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
 
 // ---- ordered compaction of the sparse children into the next wavefront --------------------------------
 __global__ void __launch_bounds__(kScanBlock) tile_sums_kernel(const uint8_t* __restrict__ nchild, long long n,
-                                                               unsigned int* __restrict__ sums) {
+                                                               unsigned int* __restrict__ sums, const Header* unseen) {
   __shared__ unsigned int s[kScanBlock / 32];
+  if (unseen) n = unseen->n_next;  // generation launched without the host knowing its size
   long long base = (long long)blockIdx.x * kTile;
   unsigned int acc = 0;
   for (int k = threadIdx.x; k < kTile; k += kScanBlock) {
@@ -520,7 +523,8 @@ __global__ void __launch_bounds__(kScanBlock) tile_sums_kernel(const uint8_t* __
 
 // single block: exclusive scan of the tile sums in place; total -> hdr->n_next; also resets the work counter
 __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restrict__ sums, int ntiles, Header* hdr,
-                                                         unsigned long long* counters, unsigned int capacity) {
+                                                         unsigned long long* counters, unsigned int capacity,
+                                                         bool unseen = false) {
   __shared__ unsigned int s[1024];
   __shared__ unsigned int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -548,6 +552,10 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restric
       atomicOr(&counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_WORK_OVERFLOW);
       total = 0;  // stop cleanly
     }
+    if (unseen) {
+      hdr->n_prev = hdr->n_next;
+      if (hdr->n_next == 0) hdr->empty_gens++;
+    }
     hdr->n_next = total;
     hdr->work_ctr = 0;
   }
@@ -557,10 +565,12 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restric
 // writes the list of occupied slots in reference (BFS) order. Thread t of a block handles entries base + sub*256 + t.
 __global__ void __launch_bounds__(kScanBlock) slots_kernel(const uint8_t* __restrict__ nchild, long long n,
                                                            const unsigned int* __restrict__ tile_base,
-                                                           uint32_t* __restrict__ slot_next, const Header* hdr) {
+                                                           uint32_t* __restrict__ slot_next, const Header* hdr,
+                                                           bool unseen) {
   __shared__ unsigned int s_warp[kScanBlock / 32];
   __shared__ unsigned int s_carry;
   if (hdr->n_next == 0) return;
+  if (unseen) n = hdr->n_prev;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_carry = tile_base[blockIdx.x];
   __syncthreads();
@@ -619,8 +629,9 @@ __global__ void sort_prep_kernel(uint32_t* __restrict__ idx, uint32_t* __restric
   }
 }
 
-__global__ void finish_kernel(unsigned long long* counters, unsigned long long gens, unsigned long long launches) {
-  counters[OPTB_C_GENERATIONS] = gens;
+__global__ void finish_kernel(unsigned long long* counters, unsigned long long gens, unsigned long long launches,
+                              const Header* hdr) {
+  counters[OPTB_C_GENERATIONS] = gens - hdr->empty_gens;
   counters[OPTB_C_LAUNCHES] = launches;
 }
 
@@ -1053,30 +1064,48 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     } else {
       a.perm = nullptr;
     }
-    long long want = (n_in + kBlock - 1) / kBlock;
-    int grid = (int)std::min<long long>(full_grid, want);
-    a.n_in = n_in;
-    void* kargs[] = {(void*)&a};
-    CK(cudaLaunchKernel((const void*)kern, dim3(grid), dim3(kBlock), kargs, smem, st), "launch trace_kernel");
-    launches++; gens++;
+    // Small wavefronts: the host round trip per generation (read the header, synchronise) costs more than the
+    // generation itself, so up to kUnseen further generations are enqueued without knowing their size. They take
+    // it from the header (at most twice the previous one, which bounds the grids) and are no-ops once the
+    // wavefront has died. Sorting needs the size on the host; the bound keeps these below the sort threshold.
+    constexpr int kUnseen = 8;
+    int unseen_left = 0;
+    if (split) {
+      long long bound = n_in;
+      while (unseen_left < kUnseen && 2 * bound < 2048 && 2 * bound <= cap) { bound *= 2; unseen_left++; }
+    }
+    long long bound = n_in;
+    for (int u = 0; u <= unseen_left; u++) {
+      const bool unseen = u > 0;
+      if (unseen) { bound *= 2; a.perm = nullptr; }
+      long long want = (bound + kBlock - 1) / kBlock;
+      int grid = (int)std::min<long long>(full_grid, want);
+      a.n_in = bound;
+      a.n_in_dev = unseen ? &hdr->n_next : nullptr;
+      void* kargs[] = {(void*)&a};
+      CK(cudaLaunchKernel((const void*)kern, dim3(grid), dim3(kBlock), kargs, smem, st), "launch trace_kernel");
+      launches++; gens++;
+      if (!split) break;
+      int ntiles = (int)((bound + kTile - 1) / kTile);
+      unsigned int* sums = (unsigned int*)(ws + L.sums);
+      tile_sums_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, bound, sums, unseen ? hdr : nullptr);
+      scan_sums_kernel<<<1, 1024, 0, st>>>(sums, ntiles, hdr, a.counters, (unsigned int)std::min<long long>(cap, 0xffffffffll), unseen);
+      // the children just written to a.c become the next generation's source; the other buffer is free again
+      uint32_t* slot_next = (uint32_t*)(ws + ((gens & 1) ? L.slot_a : L.slot_b));
+      slots_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, bound, sums, slot_next, hdr, unseen);
+      mark_kernel<<<std::min(full_grid * 2, std::max(1, (int)((2 * bound + 255) / 256))), 256, 0, st>>>(a.c.root, slot_next, hdr, (uint32_t*)a.gen_first, (uint32_t*)a.gen_last);
+      std::swap(a.w, a.c);
+      a.slot = slot_next;
+      launches += 4;
+      a.gen0 = 0;
+    }
     if (!split) break;
-    int ntiles = (int)((n_in + kTile - 1) / kTile);
-    unsigned int* sums = (unsigned int*)(ws + L.sums);
-    tile_sums_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, n_in, sums);
-    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, ntiles, hdr, a.counters, (unsigned int)std::min<long long>(cap, 0xffffffffll));
-    // the children just written to a.c become the next generation's source; the other buffer is free again
-    uint32_t* slot_next = (uint32_t*)(ws + ((gens & 1) ? L.slot_a : L.slot_b));
-    slots_kernel<<<ntiles, kScanBlock, 0, st>>>(a.nchild, n_in, sums, slot_next, hdr);
-    mark_kernel<<<std::min(full_grid * 2, std::max(1, (int)((2 * n_in + 255) / 256))), 256, 0, st>>>(a.c.root, slot_next, hdr, (uint32_t*)a.gen_first, (uint32_t*)a.gen_last);
-    std::swap(a.w, a.c);
-    a.slot = slot_next;
-    launches += 4;
+    a.n_in_dev = nullptr;
     CK(cudaMemcpyAsync(ctx->h_hdr, hdr, sizeof(Header), cudaMemcpyDeviceToHost, st), "read header");
     CK(cudaStreamSynchronize(st), "sync generation");
     n_in = ((Header*)ctx->h_hdr)->n_next;
-    a.gen0 = 0;
   }
-  finish_kernel<<<1, 1, 0, st>>>(a.counters, gens, launches + 1);
+  finish_kernel<<<1, 1, 0, st>>>(a.counters, gens, launches + 1, hdr);
   CK(cudaGetLastError(), "kernel launch");
   return 0;
 }
