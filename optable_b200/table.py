@@ -209,17 +209,63 @@ class OpticalTable:
             self.ray_tracing(batch)
             return mon1.get_yList(sort="ID"), mon1.get_tYList(sort="ID")
 
-        y0, t0 = run(work)
-        for mon, label in ((mon0, "mon0"), (mon1, "mon1")):
-            assert set(ids) == {r._id for r in mon.get_rays(sort="ID")}, f"Rays at {label} do not match the input rays."
-        pivots = mon0.get_PList(sort="ID")
         shift, axis = mon0.tangent_Y * disp, mon0.tangent_Z
-        y1, t1 = run([r._Translate(shift) for r in work])
+        both = self._abcd_first_two_traces(mon0, mon1, work, shift)
+        if both is not None:
+            # nominal and shifted bundle traced as ONE batch, rows read as columns (no segment objects); only the
+            # last trace below goes through ray_tracing and leaves table.rays / the monitors as the reference does
+            (y0, t0, pivots), (y1, t1, _) = both
+            for r in work:
+                r._Translate(shift)
+        else:
+            y0, t0 = run(work)
+            for mon, label in ((mon0, "mon0"), (mon1, "mon1")):
+                assert set(ids) == {r._id for r in mon.get_rays(sort="ID")}, f"Rays at {label} do not match the input rays."
+            pivots = mon0.get_PList(sort="ID")
+            y1, t1 = run([r._Translate(shift) for r in work])
         y2, t2 = run([r._RotAround(axis, pivots[k], rot) for k, r in enumerate(work)])
         Ms = np.zeros((len(rays), 2, 2))
         Ms[:, 0, 0], Ms[:, 1, 0] = (y1 - y0) / disp, (t1 - t0) / disp
         Ms[:, 0, 1], Ms[:, 1, 1] = (y2 - y0) / rot, (t2 - t0) / rot
         return Ms
+
+    def _abcd_first_two_traces(self, mon0, mon1, work, shift):
+        """Nominal + shifted bundle of calculate_abcd_matrix in one device call. Returns
+        ((y, tY, pivots) nominal, (y, tY, pivots) shifted), rows ordered like `work` (= by ray id), or None when
+        the shortcut would not be equivalent to three separate ray_tracing calls: other monitors on the table
+        (they would miss the rows of these traces), interact caps (counts), or a subclass overriding ray_tracing."""
+        from .backend import Engine
+
+        mine = [m for m in self.monitors if m is mon0 or m is mon1]
+        if type(self).ray_tracing is not OpticalTable.ray_tracing or len(mine) != len(self.monitors) or len(mine) != 2:
+            return None
+        flat = FlatScene(self.components, [mon0, mon1])
+        if flat.n_capslots:
+            return None
+        n = len(work)
+        batch = work + [r.copy()._Translate(shift) for r in work]
+        arrs, fam_ids, unit = pack_rays(batch)
+        engine = Engine.get()
+        scene = engine.upload(flat)
+        try:
+            out = engine.trace_arrays(scene, arrs, max_trace_num=trace_cap(None), unit=unit, record_segments=False,
+                                      n_families=len(fam_ids))
+        finally:
+            scene.close()
+        P = np.stack([out["hit_px"], out["hit_py"], out["hit_pz"]], 1)
+        D = np.stack([out["hit_dx"], out["hit_dy"], out["hit_dz"]], 1)
+        root, mon = out["hit_root"].astype(np.int64), out["hit_monitor"]
+        halves = []
+        for half in (0, 1):
+            rows0 = np.nonzero((mon == 0) & (root // n == half))[0]
+            rows1 = np.nonzero((mon == 1) & (root // n == half))[0]
+            for rows, label in ((rows0, "mon0"), (rows1, "mon1")):
+                assert set((root[rows] % n).tolist()) == set(range(n)), f"Rays at {label} do not match the input rays."
+            rows0 = rows0[np.argsort(root[rows0], kind="stable")]
+            rows1 = rows1[np.argsort(root[rows1], kind="stable")]
+            # (monitor-local point dotted with the lab tangent: the reference's get_yList, monitor.py:78-84)
+            halves.append((P[rows1] @ mon1.tangent_Y, D[rows1] @ mon1.tangent_Y, P[rows0]))
+        return halves
 
     @staticmethod
     def calibrate_symmetric_4f(lens, rays: List[Ray], F10: float, F20: float, criterion: str = "M=-I", debugaxs=None,

@@ -192,3 +192,43 @@ def test_ripa2_example_analysis_with_oracle_engine():
     np.testing.assert_allclose(got["n"], want["n"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(got["pathlength"], want["pathlength"], rtol=1e-9)
     np.testing.assert_allclose(got["roc"], want["roc"], rtol=1e-5)
+
+
+def test_abcd_matrix_batched_first_traces_equal_three_separate_traces(monkeypatch):
+    """calculate_abcd_matrix traces the nominal and the shifted bundle as one batch (columns only). Same matrices,
+    same final table state as the three separate ray_tracing calls it replaces (forced here by a third monitor on
+    the table), and the reference's own values (tests/golden/abcd_4f.npz)."""
+    import os
+
+    import optable_b200 as ob
+    from optable_b200 import backend
+    from tests import golden_io
+
+    monkeypatch.setattr(backend.Engine, "get", classmethod(lambda cls, device=None: OracleEngine()))
+    z = np.load(os.path.join(golden_io.GOLDEN_DIR, "abcd_4f.npz"))
+    F1, F2 = z["F"]
+
+    def build(extra_monitor):
+        lens = scenes.asphere_lens9(ob, [43.17, 0, 0])
+        l0 = lens.copy()._Translate(np.array([F1, 0, 0]) - lens.origin)
+        l1 = lens.copy()._Translate(np.array([F1 + 2 * F2, 0, 0]) - lens.origin).RotZ(np.pi)
+        m0, m1 = ob.Monitor(origin=[0, 0, 0], width=5, height=5), ob.Monitor(origin=[2 * F1 + 2 * F2, 0, 0], width=5, height=5)
+        table = ob.OpticalTable()
+        table.add_components([l0, l1])
+        table.add_monitors([m0, m1] + ([ob.Monitor(origin=[-5, 0, 0], width=1, height=1)] if extra_monitor else []))
+        return table, m0, m1
+
+    fast_t, fm0, fm1 = build(False)
+    slow_t, sm0, sm1 = build(True)
+    calls = []
+    real = ob.OpticalTable.ray_tracing
+    monkeypatch.setattr(ob.OpticalTable, "ray_tracing", lambda self, rays, perfomance_limit=None: (calls.append(self), real(self, rays, perfomance_limit))[1])
+    # (the wrapper is installed on the class, so `type(self).ray_tracing is OpticalTable.ray_tracing` still holds)
+    Mf = fast_t.calculate_abcd_matrix(fm0, fm1, scenes.abcd_rays(ob))
+    Ms = slow_t.calculate_abcd_matrix(sm0, sm1, scenes.abcd_rays(ob))
+    assert calls.count(fast_t) == 1 and calls.count(slow_t) == 3
+    np.testing.assert_allclose(Mf, Ms, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(Mf, z["Ms"], rtol=1e-5, atol=2e-4)
+    assert len(fast_t.rays) == len(slow_t.rays) and fm1.ndata == sm1.ndata == 7
+    np.testing.assert_allclose(fm1.get_yList(sort="ID"), sm1.get_yList(sort="ID"), rtol=0, atol=1e-15)
+    np.testing.assert_allclose([r.origin for r in fast_t.rays], [r.origin for r in slow_t.rays], rtol=0, atol=1e-15)
