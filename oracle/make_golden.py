@@ -67,8 +67,10 @@ def make_abcd():
     table.ray_tracing(rays)
     y, ty = m1.get_yList(), m1.get_tYList()
     Ms = table.calculate_abcd_matrix(m0, m1, rays)
+    # the full Nelder-Mead calibration of the example (optimize=True does not render; ~30 s of reference time)
+    F_opt = ref.OpticalTable.calibrate_symmetric_4f(lens, scenes.abcd_rays(ref), F10=F1, F20=F2, criterion="M=-I", optimize=True)
     np.savez_compressed(os.path.join(OUT, "abcd_4f.npz"), Ms=np.asarray(Ms), yList=np.asarray(y), tYList=np.asarray(ty),
-                        F=np.array([F1, F2]))
+                        F=np.array([F1, F2]), F_opt=np.asarray(F_opt, dtype=float))
     return np.asarray(Ms)
 
 

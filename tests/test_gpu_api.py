@@ -112,6 +112,9 @@ def test_abcd_matrix_and_4f_calibration_callers():
     assert Ms.shape == (7, 2, 2) and abs(Ms[3, 0, 0] + 1) < 0.2   # a 4f relay images with magnification about -1
     F = ob.OpticalTable.calibrate_symmetric_4f(lens, rays[2:5], F10=F1, F20=F2, criterion="min_stdtY", optimize=True)
     assert len(F) == 2 and all(np.isfinite(F)) and abs(F[0] - F1) < 5
+    # the whole Nelder-Mead calibration (94 cost evaluations x 2 device calls) lands where the reference's does
+    F = ob.OpticalTable.calibrate_symmetric_4f(lens, scenes.abcd_rays(ob), F10=F1, F20=F2, criterion="M=-I", optimize=True)
+    np.testing.assert_allclose(F, z["F_opt"], rtol=1e-6)
 
 
 def test_scene_upload_rejects_malformed_tables():
