@@ -192,3 +192,47 @@ def test_ripa2_example_with_its_analysis():
     np.testing.assert_allclose(got["n"], want["n"], rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(got["pathlength"], want["pathlength"], rtol=1e-9)
     np.testing.assert_allclose(got["roc"], want["roc"], rtol=1e-5)   # q behind finite-difference asphere curvatures
+
+
+def test_device_monitor_analytics_match_host_monitor(tmp_path):
+    """optable_b200.analytics.DeviceMonitor (rows stay in HBM) against the host Monitor fed the same rows."""
+    import torch
+
+    from optable_b200.analytics import DeviceMonitor
+    from optable_b200.bundle import RayBundle
+
+    sc = scenes.telescope_4f(ob)
+    table = ob.OpticalTable()
+    table.add_components(sc.components)
+    table.add_monitors(sc.monitors)
+    bundle = RayBundle.collimated_disc(20000, radius=2.0)
+    out = table.trace_bundle(bundle, record_hist=True)
+    for m, mon in enumerate(table.monitors):
+        dm = DeviceMonitor(mon, out, m)
+        sel = (out["hit_monitor"] == m).cpu().numpy()
+        h = {k: out[k].cpu().numpy()[sel] for k in out if k.startswith("hit_")}
+        host = ob.Monitor(origin=mon.origin, width=mon.width, height=mon.height)
+        host.transform_matrix = mon.transform_matrix
+        host._extend(np.stack([h["hit_px"], h["hit_py"], h["hit_pz"]], 1), h["hit_intensity"], h["hit_t"],
+                     np.stack([h["hit_dx"], h["hit_dy"], h["hit_dz"]], 1), h["hit_q_re"] + 1j * h["hit_q_im"],
+                     h["hit_root"].astype(np.int64).tolist())
+        assert dm.ndata == host.ndata > 1000
+        for name in ("get_yList", "get_zList", "get_tYList", "get_tZList", "get_IList", "get_tList"):
+            for sort in ("YZ", "ID"):
+                np.testing.assert_allclose(getattr(dm, name)(sort=sort).cpu().numpy(), getattr(host, name)(sort=sort), rtol=1e-14,
+                                           atol=1e-16, err_msg=f"{name}/{sort}")
+        np.testing.assert_allclose(dm.get_waist_distance().cpu().numpy(), host.get_waist_distance(), rtol=1e-14)
+        assert float(dm.sum_intensity) == pytest.approx(host.sum_intensity, rel=1e-12)
+        assert float(dm.std_histy) == pytest.approx(host.std_histy, rel=1e-12)
+        counts, _ = host._get_hist_y()
+        np.testing.assert_array_equal(dm._get_hist_y()[0].cpu().numpy(), counts)
+        dm.hist_y = None                                     # the binning fallback without the trace's histogram
+        np.testing.assert_array_equal(dm._get_hist_y()[0].cpu().numpy(), counts)
+        dy, dz = dm.get_delta_pos()
+        hy, hz = host.get_delta_pos()
+        np.testing.assert_allclose(dy.cpu().numpy(), hy, rtol=0, atol=1e-15)
+        dm.export_rays_npz(str(tmp_path / f"m{m}.npz"))
+        host.export_rays_npz(str(tmp_path / f"h{m}.npz"))
+        a, b = np.load(tmp_path / f"m{m}.npz"), np.load(tmp_path / f"h{m}.npz")
+        for k in b.files:
+            np.testing.assert_allclose(a[k], b[k], rtol=1e-14, atol=1e-16)
