@@ -236,3 +236,27 @@ def test_device_monitor_analytics_match_host_monitor(tmp_path):
         a, b = np.load(tmp_path / f"m{m}.npz"), np.load(tmp_path / f"h{m}.npz")
         for k in b.files:
             np.testing.assert_allclose(a[k], b[k], rtol=1e-14, atol=1e-16)
+
+
+def test_bench_line_contract_small():
+    """bench.py end to end on a small bundle: one JSON line carrying every key of the contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--rays", "200000", "--steps", "3", "--warmup", "3",
+                          "--e2e-steps", "1", "--cpu-rays", "500"], capture_output=True, text=True, cwd=root, timeout=600)
+    assert run.returncode == 0, run.stderr[-2000:]
+    lines = [l for l in run.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] > 0 and d["value"] > 1e8
+    assert d["e2e"]["value"] > 1e7 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and 0 < d["roofline"]["frac"] < 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["config"]["interactions_per_step_per_gpu"] == 4 * 200000
