@@ -10,6 +10,9 @@ from __future__ import annotations
 import numpy as np
 
 RTOL = 1e-9
+# Distances along a ray are compared relative to max(|t|, LENGTH_FLOOR): the reference takes a curved-surface hit from
+# scipy's brentq with xtol = 2e-12 (absolute), so its own t is only defined to 2e-12; RTOL * LENGTH_FLOOR is that.
+LENGTH_FLOOR = 2e-3
 
 
 def _rel_vec(a, b, floor):
@@ -40,7 +43,7 @@ def compare(ref, got, rtol=RTOL, q_rtol=None, label=""):
     if len(ref["seg_root"]):
         errs["seg_o"] = _rel_vec(ref["seg_o"], got["seg_o"], 1.0).max()
         errs["seg_d"] = _rel_vec(ref["seg_d"], got["seg_d"], 1.0).max()
-        errs["seg_length"] = _rel(ref["seg_length"], got["seg_length"], 1e-3).max()
+        errs["seg_length"] = _rel(ref["seg_length"], got["seg_length"], LENGTH_FLOOR).max()
         errs["seg_intensity"] = _rel(ref["seg_intensity"], got["seg_intensity"]).max()
         errs["seg_wavelength"] = _rel(ref["seg_wavelength"], got["seg_wavelength"]).max()
         errs["seg_pathlength"] = _rel(ref["seg_pathlength"], got["seg_pathlength"], 1e-3).max()
@@ -56,7 +59,7 @@ def compare(ref, got, rtol=RTOL, q_rtol=None, label=""):
         assert bad.size == 0, f"{label}: {k} differs at rows {bad[:8]}"
     if len(ref["hit_root"]):
         errs["hit_P"] = _rel_vec(ref["hit_P"], got["hit_P"], 1.0).max()
-        errs["hit_t"] = _rel(ref["hit_t"], got["hit_t"], 1e-3).max()
+        errs["hit_t"] = _rel(ref["hit_t"], got["hit_t"], LENGTH_FLOOR).max()
         errs["hit_intensity"] = _rel(ref["hit_intensity"], got["hit_intensity"]).max()
         errs["hit_d"] = _rel_vec(ref["hit_d"], got["hit_d"], 1.0).max()
     for k, v in errs.items():
