@@ -71,6 +71,13 @@ class OpticalComponent(Vector):
         self.origin = pivot(self.origin, R, localpoint)
         return self
 
+    def interact(self, ray, engine=None):
+        """One pop of the bounce loop against this component (or group) alone, on the device: (t, [truncated
+        parent, children...]) or (None, None), like optical_component.py:337-378 / component_group.py:93-122."""
+        from .table import single_pop
+
+        return single_pop(self, ray, engine)
+
     def gather_components(self, avoid_flatten_classname=(), ignore_classname=()):
         """Flat description rows of this component tree for the CSV export (optical_component.py:386-426)."""
         from .export import component_rows

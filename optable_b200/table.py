@@ -142,6 +142,54 @@ def trace_table(table, rays, perfomance_limit=None, engine=None):
     return segs
 
 
+def single_pop(component, ray, engine=None):
+    """`component.interact(ray)` of the reference (optical_component.py:337-378, component_group.py:93-122) for one
+    component or group: one pop of the bounce loop against this component alone, on the device.
+    Returns (t, [truncated parent, child rays...]) or (None, None). Interact counts of capped leaves are updated
+    for this pop only, like the reference's.
+
+    Two device calls: with a pop budget of 1 the children are queued and dropped, which yields t, the count update
+    and (from the dropped counter) the number of children; a second call with budget 1 + children, on a scratch
+    count table, pops the children so that their state can be read from their segment rows."""
+    from .backend import Engine
+
+    if not ray.alive:
+        return None, None
+    engine = engine or Engine.get()
+    flat = FlatScene([component], [])
+    arrs, fam_ids, unit = pack_rays([ray])
+    caps = None
+    if flat.n_capslots:
+        caps = np.array([[c._interact_count.get(ray._id, 0)] for c in flat.capslots], np.int32)
+    scene = engine.upload(flat)
+    try:
+        first = engine.trace_arrays(scene, arrs, max_trace_num=1, unit=unit, n_families=1, cap_counts=caps)
+        if int(first["seg_leaf"][0]) < 0:
+            return None, None
+        if flat.n_capslots:
+            for s, comp in enumerate(flat.capslots):
+                if first["cap_counts"][s, 0]:
+                    comp._interact_count[ray._id] = int(first["cap_counts"][s, 0])
+        t = float(first["seg_length"][0])
+        n_children = int(first["counters"][A.C_DROPPED])
+        out = [ray.copy(length=t, alive=False)]
+        if n_children:
+            again = engine.trace_arrays(scene, arrs, max_trace_num=1 + n_children, unit=unit, n_families=1, cap_counts=caps)
+            for k in range(1, 1 + n_children):
+                hasq = bool(again["seg_flags"][k] & A.RF_HASQ)
+                child = ray.copy(alive=True)
+                child.origin = np.array([again["seg_ox"][k], again["seg_oy"][k], again["seg_oz"][k]])
+                child._direction = np.array([again["seg_dx"][k], again["seg_dy"][k], again["seg_dz"][k]])
+                child.intensity = float(again["seg_intensity"][k])
+                child.qo = complex(again["seg_q_re"][k], again["seg_q_im"][k]) if hasq else None
+                child._pathlength = float(again["seg_pathlength"][k])
+                child._n = float(again["seg_n"][k])
+                out.append(child)
+    finally:
+        scene.close()
+    return t, out
+
+
 class OpticalTable:
     def __init__(self, **kwargs):
         self.components = []

@@ -260,3 +260,27 @@ def test_bench_line_contract_small():
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and 0 < d["roofline"]["frac"] < 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["config"]["interactions_per_step_per_gpu"] == 4 * 200000
+
+
+def test_component_interact_single_pop_on_device():
+    """`component.interact(ray)`: one pop against one component/group on the device, against the oracle engine."""
+    from tests.test_install_cpu import OracleEngine
+
+    hits = 0
+    for name in ("misc_components", "prism_refl", "doublet"):
+        a, b = scenes.REGISTRY[name](ob), scenes.REGISTRY[name](ob)
+        for ca, cb in zip(a.components, b.components):
+            for ra, rb in list(zip(a.rays, b.rays))[:5]:
+                tw, rw = ca.interact(ra, engine=OracleEngine())
+                tg, rg = cb.interact(rb)
+                assert (tw is None) == (tg is None)
+                if tw is None:
+                    continue
+                hits += 1
+                assert tg == pytest.approx(tw, rel=1e-9) and len(rg) == len(rw)
+                for x, y in zip(rw, rg):
+                    np.testing.assert_allclose(y.origin, x.origin, rtol=1e-9, atol=1e-12)
+                    np.testing.assert_allclose(y.direction, x.direction, rtol=1e-9, atol=1e-12)
+                    assert y.alive == x.alive and y.intensity == pytest.approx(x.intensity, rel=1e-9, abs=1e-300)
+                    assert y.length == x.length or y.length == pytest.approx(x.length, rel=1e-9)
+    assert hits > 10

@@ -232,3 +232,37 @@ def test_abcd_matrix_batched_first_traces_equal_three_separate_traces(monkeypatc
     assert len(fast_t.rays) == len(slow_t.rays) and fm1.ndata == sm1.ndata == 7
     np.testing.assert_allclose(fm1.get_yList(sort="ID"), sm1.get_yList(sort="ID"), rtol=0, atol=1e-15)
     np.testing.assert_allclose([r.origin for r in fast_t.rays], [r.origin for r in slow_t.rays], rtol=0, atol=1e-15)
+
+
+def test_component_interact_single_pop_equals_reference():
+    """`component.interact(ray)` (one pop against one component or group, optical_component.py:337-378) through the
+    device path (oracle engine here): t, the truncated parent and every child ray against the reference's."""
+    import optable_b200 as ob
+
+    ref = RH.load_reference()
+    rng = np.random.default_rng(5)
+    n_checked = n_hits = 0
+    for name in ("misc_components", "doublet", "telescope_4f", "prism_refl", "extras"):
+        a, b = scenes.REGISTRY[name](ref), scenes.REGISTRY[name](ob)
+        for ca, cb in zip(a.components, b.components):
+            for ra, rb in list(zip(a.rays, b.rays))[:6]:
+                tw, rw = ca.interact(ra)
+                tg, rg = cb.interact(rb, engine=OracleEngine())
+                n_checked += 1
+                assert (tw is None) == (tg is None), (name, type(ca).__name__)
+                if tw is None:
+                    assert rg is None
+                    continue
+                n_hits += 1
+                assert tg == pytest.approx(tw, rel=1e-9) and len(rg) == len(rw)
+                for x, y in zip(rw, rg):
+                    fx, fy = _fields(x), _fields(y)
+                    assert parity._rel_vec(fx[0], fy[0], 1.0) <= 1e-9 and parity._rel_vec(fx[1], fy[1], 1.0) <= 1e-9
+                    assert (fx[2] is None) == (fy[2] is None) and (fx[2] is None or abs(fx[2] - fy[2]) <= 1e-9 * max(abs(fx[2]), 1e-3))
+                    assert fx[3] == fy[3] and fx[4] == pytest.approx(fy[4], rel=1e-9, abs=1e-300) and fx[5] == fy[5]
+                    assert (fx[6] is None) == (fy[6] is None) and (fx[6] is None or abs(fx[6] - fy[6]) <= 1e-6 * abs(fx[6]))
+                    assert fx[7] == pytest.approx(fy[7], rel=1e-9, abs=1e-12) and fx[8] == pytest.approx(fy[8], rel=1e-12)
+        leaves_a, leaves_b = RH._leaves(a.components, []), RH._leaves(b.components, [])
+        for la, lb in zip(leaves_a, leaves_b):   # interact counts moved the same way
+            assert la.max_interact_count is None or sorted(la._interact_count.values()) == sorted(lb._interact_count.values())
+    assert n_checked > 100 and n_hits > 20
