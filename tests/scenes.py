@@ -408,7 +408,7 @@ def ripa2_postprocess(ns, table, scene):
     return {"P": np.array(P), "n": np.array(nrm), "roc": np.array(roc), "pathlength": np.array(pl)}
 
 
-def fuzz(ns, seed, n_rays=24):
+def fuzz(ns, seed, n_rays=24, caps=False):
     """Random scene for the fuzz parity tests: 4-9 components drawn from the whole component zoo with random
     parameters, positions in a 15 x 5 x 1.6 box, mostly facing the beam, 2 monitors, a cone of rays from the
     left (3 wavelengths, some without q, some length-limited). Deterministic in `seed`; both packages build the
@@ -469,6 +469,22 @@ def fuzz(ns, seed, n_rays=24):
         d = [1.0, 0.12 * rng.standard_normal(), 0.04 * rng.standard_normal()]
         rays.append(ns.Ray([U(-1, 1), U(-1.5, 1.5), U(-0.5, 0.5)], d, intensity=U(0.2, 1.0), **kw))
     mons = [place(ns.Monitor(pos(), U(4, 12), U(4, 12))), ns.Monitor([20, 0, 0], 30, 12)]
+    if caps:
+        # binding interact caps: a third of the leaves stop interacting after 1-3 hits per ray id, and
+        # the rays come in families of three wavelengths sharing one id, so the outcome depends on the reference's
+        # sequential order across the rays of a family and across pops
+        def leaves(cs, out):
+            for c in cs:
+                leaves(c.components, out) if hasattr(c, "components") else out.append(c)
+            return out
+
+        for leaf in leaves(comps, []):
+            if U() < 0.33:
+                leaf.max_interact_count = int(rng.integers(1, 4))
+        fam = []
+        for k, r in enumerate(rays[: max(3, n_rays // 3)]):
+            fam += [r.copy(wavelength=w, id=1000 + k) if hasattr(r, "copy") else r for w in wls]
+        rays = fam
     return Scene(comps, rays, mons, limit={"max_trace_num": 60})
 
 

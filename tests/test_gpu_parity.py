@@ -89,3 +89,30 @@ def test_fuzz_scenes_cuda_equals_oracle(engine, block):
         rays += len(batch["ox"])
     # equal-distance ties between coplanar overlapping apertures: a few per 1e4 rays
     assert pops > 5000 and restarted > 4000 and flagged <= 2e-3 * rays, (flagged, rays)
+
+
+def test_fuzz_scenes_with_binding_interact_caps(engine):
+    """Random scenes with binding max_interact_count and ray families sharing an id (tests/scenes.fuzz(caps=True)):
+    the family-serial kernel against the oracle, interact-count tables included."""
+    import optable_b200 as ob
+    from optable_b200.flatten import FlatScene, pack_rays, trace_cap
+    from oracle import oracle as O
+    from oracle import ref_harness as RH
+    from tests import scenes
+
+    reached = flagged = 0
+    for seed in range(300, 340):
+        sc = scenes.fuzz(ob, seed, caps=True)
+        flat = FlatScene(sc.components, sc.monitors)
+        arrs, fam_ids, unit = pack_rays(sc.rays)
+        params = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
+        raw = O.trace(flat, arrs, **params)
+        out, got = _gpu(engine, flat, arrs, params)
+        _, ties = parity.compare_flagging_ties(flat, RH.arrays_from_result(raw), got, rtol=FUZZ_PATH_RTOL,
+                                               q_rtol=10 * max(_q_rtol(flat), FUZZ_PATH_RTOL), label=f"caps fuzz seed {seed}")
+        flagged += len(ties)
+        if flat.n_capslots and not ties:
+            np.testing.assert_array_equal(out["cap_counts"], raw["cap_counts"])
+            capmax = flat.node_f[flat.node_i[:, 6] >= 0, 39]
+            reached += int((raw["cap_counts"].max(axis=1) >= capmax).any())
+    assert reached > 20 and flagged <= 3

@@ -41,3 +41,26 @@ def test_fuzz_scenes_oracle_equals_reference(block):
         flagged += len(ties)
         rays += len(sc.rays)
     assert flagged <= max(1, 2e-3 * rays)
+
+
+def test_fuzz_scenes_with_binding_interact_caps():
+    """Random scenes in which a third of the leaves carry max_interact_count 1-3 and rays come in three-wavelength
+    families sharing one id (tests/scenes.fuzz(caps=True)): the visible set depends on the reference's sequential
+    order. Oracle against the live reference, interact-count tables included."""
+    import numpy as np
+
+    ref = RH.load_reference()
+    reached = 0
+    for seed in range(300, 316):
+        sc = scenes.fuzz(ref, seed, caps=True)
+        flat = FlatScene(sc.components, sc.monitors)
+        arrs, fam_ids, unit = pack_rays(sc.rays)
+        want = RH.run_reference(sc)
+        want.pop("_leaves", None)
+        got = O.trace(flat, arrs, max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
+        parity.compare_flagging_ties(flat, want, RH.arrays_from_result(got), q_rtol=1e-5, label=f"caps fuzz seed {seed}")
+        for s, comp in enumerate(flat.capslots):
+            for f, rid in enumerate(fam_ids):
+                assert got["cap_counts"][s, f] == comp._interact_count.get(rid, 0)
+            reached += int(got["cap_counts"][s].max() >= comp.max_interact_count)
+    assert reached > 10
