@@ -71,3 +71,41 @@ def test_error_behaviour_matches_reference():
         FlatScene([ob.BaseRefraciveSurface([0, 0, 0], n1=1, n2=1.5)])  # bare Plane has no boundary
     with pytest.raises(FlattenError):
         FlatScene([ob.CircleRefractive([0, 0, 0], n1=ob.Material("x", lambda wl: 1.5), n2=1)])
+
+
+def _compare_flat(flat, want_flat):
+    from optable_b200 import _abi as A
+
+    cols = [A.NI_GEOM, A.NI_INTER, A.NI_AABB, A.NI_MAT1, A.NI_MAT2, A.NI_CAPSLOT, A.NI_AUX, A.NI_ROCKIND, A.NI_LEAF]
+    mine, ref = flat.node_i[:, A.NI_LEAF] >= 0, want_flat.node_i[:, A.NI_LEAF] >= 0
+    assert flat.n_leaves == want_flat.n_leaves == int(mine.sum()) == int(ref.sum())
+    np.testing.assert_array_equal(flat.node_i[mine][:, cols], want_flat.node_i[ref][:, cols])
+    np.testing.assert_allclose(flat.node_f[mine], want_flat.node_f[ref], rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(flat.mat_kind, want_flat.mat_kind)
+    np.testing.assert_allclose(flat.mat_f, want_flat.mat_f, rtol=1e-15, atol=0)
+    np.testing.assert_allclose(flat.mon_f, want_flat.mon_f, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(flat.aux, want_flat.aux, rtol=1e-12, atol=1e-12)
+    assert flat.max_children == want_flat.max_children and flat.n_capslots == want_flat.n_capslots
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_constructions_match_reference_classes(block):
+    """Every component class with random constructor arguments and poses (tests/scenes.fuzz, 200 scenes, with and
+    without interact caps): this package's classes and the reference's flatten to the same tables."""
+    from oracle import ref_harness as RH
+
+    if not RH.reference_available():
+        pytest.skip("/root/reference not present")
+    ref = RH.load_reference()
+    for seed in range(7000 + 50 * block, 7050 + 50 * block):
+        caps = bool(seed % 2)
+        a, b = scenes.fuzz(ref, seed, caps=caps), scenes.fuzz(ob, seed, caps=caps)
+        _compare_flat(FlatScene(b.components, b.monitors), FlatScene(a.components, a.monitors))
+        ra, fa, ua = pack_rays(a.rays)
+        rb, fb, ub = pack_rays(b.rays)
+        assert ua == ub and len(fa) == len(fb)
+        for k in ra:
+            if ra[k].dtype.kind == "f":
+                np.testing.assert_allclose(rb[k], ra[k], rtol=1e-13, atol=1e-15)
+            else:
+                np.testing.assert_array_equal(rb[k], ra[k])
