@@ -408,7 +408,7 @@ def ripa2_postprocess(ns, table, scene):
     return {"P": np.array(P), "n": np.array(nrm), "roc": np.array(roc), "pathlength": np.array(pl)}
 
 
-def fuzz(ns, seed, n_rays=24, caps=False):
+def fuzz(ns, seed, n_rays=24, caps=False, extended=False):
     """Random scene for the fuzz parity tests: 4-9 components drawn from the whole component zoo with random
     parameters, positions in a 15 x 5 x 1.6 box, mostly facing the beam, 2 monitors, a cone of rays from the
     left (3 wavelengths, some without q, some length-limited). Deterministic in `seed`; both packages build the
@@ -452,6 +452,22 @@ def fuzz(ns, seed, n_rays=24, caps=False):
         lambda: ns.SphereRefractive(pos(), radius=U(2.0, 6.0), height=U(0.5, 1.5), n1=1.0, n2=1.0 + U(0.3, 0.8),
                                     reflectivity=U(0.0, 0.15)),
     ]
+    if extended:
+        # the rest of the zoo (CPU-side tests only: the GPU fuzz tests keep the scenes their seeds have always meant)
+        palette += [
+            lambda: ns.MMA(pos(), N=(int(rng.integers(2, 5)), int(rng.integers(1, 4))), pitch=U(0.4, 0.8), roc=U(3, 12), n=1.0 + U(0.4, 0.6),
+                           thickness=U(0.2, 0.6)),
+            lambda: ns.MirrorPair(pos(), width=U(1.5, 3), height=U(1.5, 3), angle=U(1.2, 1.9), reflectivity_1=U(0.5, 1.0),
+                                  transmission_2=U(0.0, 0.4)),
+            lambda: ns.MirrorPrism(pos(), width=U(1.5, 3), height=U(1.5, 3), angle=U(1.2, 1.9), reflectivity=U(0.6, 1.0)),
+            lambda: ns.TriangularPrism(pos(), width=U(1.5, 3), height=U(1.5, 3), n1=1.0, n2=ns.Glass_NBK7(), alpha=U(0.6, 1.0),
+                                       beta=U(1.2, 1.7), reflectivity_1=U(0.0, 0.3), reflectivity_2=U(0.0, 0.5),
+                                       max_interact_count_2=int(rng.integers(2, 6)), max_interact_count_3=int(rng.integers(2, 6))),
+            lambda: ns.DovePrism(pos(), L=U(3, 5), D=U(0.8, 1.2), Ng=1.0 + U(0.4, 0.6)),
+            lambda: ns.ASphericExactSphericalLens(pos(), EFL=U(6, 15), CT=U(0.5, 0.9), diameter=U(2.0, 3.0), n=1.0 + U(0.4, 0.7)),
+            lambda: ns.SquareRefractive(pos(), width=U(1.5, 4), height=U(1.5, 4), n1=1.0, n2=1.0 + U(0.3, 0.8), reflectivity=U(0.0, 0.3)),
+            lambda: ns.CircleRefractive(pos(), radius=U(0.8, 2.0), n1=1.0 + U(0.0, 0.5), n2=1.0 + U(0.3, 0.8), reflectivity=U(0.0, 0.3)),
+        ]
     comps = []
     for k in rng.choice(len(palette), size=int(rng.integers(4, 10))):
         c = place(palette[int(k)]())

@@ -64,3 +64,26 @@ def test_fuzz_scenes_with_binding_interact_caps():
                 assert got["cap_counts"][s, f] == comp._interact_count.get(rid, 0)
             reached += int(got["cap_counts"][s].max() >= comp.max_interact_count)
     assert reached > 10
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_fuzz_scenes_whole_zoo(block):
+    """tests/scenes.fuzz(extended=True): the remaining component classes (MMA, MirrorPair, MirrorPrism,
+    TriangularPrism with its built-in caps, DovePrism polygons, the exact-spherical asphere, bare refractive faces)
+    mixed into the random scenes, every third scene with binding caps. Fields behind finite-difference aspheres
+    (normal and curvature from numerical derivatives, surfaces.py:351-369) are compared to 1e-6 along whole paths."""
+    ref = RH.load_reference()
+    for seed in range(800 + 12 * block, 812 + 12 * block):
+        caps = seed % 3 == 0
+        sc = scenes.fuzz(ref, seed, caps=caps, extended=True)
+        flat = FlatScene(sc.components, sc.monitors)
+        arrs, fam_ids, unit = pack_rays(sc.rays)
+        want = RH.run_reference(sc)
+        want.pop("_leaves", None)
+        got = O.trace(flat, arrs, max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
+        fd = parity.q_rtol_for(flat) > parity.RTOL
+        parity.compare_flagging_ties(flat, want, RH.arrays_from_result(got), rtol=1e-6 if fd else parity.RTOL,
+                                     q_rtol=1e-5 if fd else parity.RTOL, label=f"zoo fuzz seed {seed}")
+        for s, comp in enumerate(flat.capslots):
+            for f, rid in enumerate(fam_ids):
+                assert got["cap_counts"][s, f] == comp._interact_count.get(rid, 0)

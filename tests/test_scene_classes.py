@@ -98,8 +98,8 @@ def test_random_constructions_match_reference_classes(block):
         pytest.skip("/root/reference not present")
     ref = RH.load_reference()
     for seed in range(7000 + 50 * block, 7050 + 50 * block):
-        caps = bool(seed % 2)
-        a, b = scenes.fuzz(ref, seed, caps=caps), scenes.fuzz(ob, seed, caps=caps)
+        caps, extended = bool(seed % 2), bool(seed % 4 < 2)   # extended: the whole zoo incl. MMA, roof mirrors, prisms
+        a, b = scenes.fuzz(ref, seed, caps=caps, extended=extended), scenes.fuzz(ob, seed, caps=caps, extended=extended)
         _compare_flat(FlatScene(b.components, b.monitors), FlatScene(a.components, a.monitors))
         ra, fa, ua = pack_rays(a.rays)
         rb, fb, ub = pack_rays(b.rays)
