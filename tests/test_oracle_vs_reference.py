@@ -36,8 +36,9 @@ def test_fuzz_scenes_oracle_equals_reference(block):
         arrs, fam_ids, unit = pack_rays(sc.rays)
         want = RH.run_reference(sc)
         got = O.trace(flat, arrs, max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
-        q_rtol = 1e-5 if parity.q_rtol_for(flat) > parity.RTOL else parity.RTOL
-        _, ties = parity.compare_flagging_ties(flat, want, RH.arrays_from_result(got), q_rtol=q_rtol, label=f"fuzz seed {seed}")
+        fd = parity.q_rtol_for(flat) > parity.RTOL   # finite-difference asphere normals/curvatures: 1e-6 along whole paths
+        _, ties = parity.compare_flagging_ties(flat, want, RH.arrays_from_result(got), rtol=1e-6 if fd else parity.RTOL,
+                                               q_rtol=1e-4 if fd else parity.RTOL, label=f"fuzz seed {seed}")
         flagged += len(ties)
         rays += len(sc.rays)
     assert flagged <= max(1, 2e-3 * rays)
@@ -83,7 +84,7 @@ def test_fuzz_scenes_whole_zoo(block):
         got = O.trace(flat, arrs, max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
         fd = parity.q_rtol_for(flat) > parity.RTOL
         parity.compare_flagging_ties(flat, want, RH.arrays_from_result(got), rtol=1e-6 if fd else parity.RTOL,
-                                     q_rtol=1e-5 if fd else parity.RTOL, label=f"zoo fuzz seed {seed}")
+                                     q_rtol=1e-4 if fd else parity.RTOL, label=f"zoo fuzz seed {seed}")
         for s, comp in enumerate(flat.capslots):
             for f, rid in enumerate(fam_ids):
                 assert got["cap_counts"][s, f] == comp._interact_count.get(rid, 0)
