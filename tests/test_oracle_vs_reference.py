@@ -23,11 +23,11 @@ def test_oracle_vs_live_reference(name, capsys):
 
 @pytest.mark.parametrize("block", range(6))
 def test_fuzz_scenes_oracle_equals_reference(block):
-    """Random scenes over the whole component zoo (tests/scenes.fuzz): 60 scenes here; 2,900 were run when the
-    generator was written (529,240 segments): no index, pop-count or tolerance difference except 7 initial rays at
+    """Random scenes over the whole component zoo (tests/scenes.fuzz): 60 scenes here; 8,900 were run when the
+    generator was written (1.69 million segments): no index or pop-count difference except 33 initial rays at
     equal-distance ties between overlapping coplanar lenslets (parity.compare_flagging_ties), where numpy's and the
-    C restatement's last bit of t decide differently, and q at 4e-6 in one scene behind rotated finite-difference
-    aspheres (parity.q_rtol_for)."""
+    C restatement's last bit of t decide differently; fields within 1e-9 except behind rotated finite-difference
+    aspheres (q 4e-6 once) and 1.0-1.4e-9 on a length in 3 scenes (profiles/r1_parity_sweep.md)."""
     ref = RH.load_reference()
     flagged = rays = 0
     for seed in range(100 + 10 * block, 110 + 10 * block):
