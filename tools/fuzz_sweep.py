@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""CUDA vs oracle on many random scenes (tests/scenes.fuzz): python tools/fuzz_sweep.py FIRST_SEED N_SCENES [n_rays]"""
+"""CUDA vs oracle on many random scenes (tests/scenes.fuzz):
+  python tools/fuzz_sweep.py FIRST_SEED N_SCENES [n_rays] [--extended] [--caps]
+(--extended / --caps scenes have so far only been run oracle-vs-reference on the CPU and, for --caps, on 40 scenes on the GPU.)"""
 import os, sys, time, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -9,8 +11,11 @@ from optable_b200.flatten import FlatScene, pack_rays, trace_cap
 from oracle import oracle as O, ref_harness as RH
 from tests import parity, scenes
 
-first, count = int(sys.argv[1]), int(sys.argv[2])
-n_rays = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+flags = {a for a in sys.argv[1:] if a.startswith("--")}   # --extended: the whole component zoo; --caps: binding interact caps
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+first, count = int(argv[0]), int(argv[1])
+n_rays = int(argv[2]) if len(argv) > 2 else 64
+EXTENDED, CAPS = "--extended" in flags, "--caps" in flags
 e = Engine.get(0)
 pops = rays = hits = 0
 flagged, failures, worst = [], [], collections.defaultdict(float)
@@ -18,7 +23,7 @@ flagged1, worst1, pops1, rays1 = [], collections.defaultdict(float), 0, 0
 kinds = collections.Counter()
 t0 = time.time()
 for seed in range(first, first + count):
-    sc = scenes.fuzz(ob, seed, n_rays=n_rays)
+    sc = scenes.fuzz(ob, seed, n_rays=n_rays, caps=CAPS, extended=EXTENDED)
     flat = FlatScene(sc.components, sc.monitors)
     arrs, fam, unit = pack_rays(sc.rays)
     prm = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam))
