@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """CUDA vs oracle on many random scenes (tests/scenes.fuzz):
   python tools/fuzz_sweep.py FIRST_SEED N_SCENES [n_rays] [--extended] [--caps]
-(--extended / --caps scenes have so far only been run oracle-vs-reference on the CPU and, for --caps, on 40 scenes on the GPU.)"""
+(on the GPU so far: 300 --extended scenes, 40 --caps scenes; see profiles/r1_parity_sweep.md)"""
 import os, sys, time, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
