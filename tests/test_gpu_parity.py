@@ -47,15 +47,9 @@ def test_wavefront_scheduling_does_not_change_results(engine, name, chain_len):
 FUZZ_PATH_RTOL = 1e-6
 
 
-@pytest.mark.parametrize("block", range(6))
-def test_fuzz_scenes_cuda_equals_oracle(engine, block):
-    """300 random scenes over the whole component zoo (tests/scenes.fuzz, 64 rays each, built with this package's
-    classes), CUDA path through the C ABI against the C oracle.
-    (a) Whole paths (up to 60 pops, splitting): winning leaf, pop numbering and segment counts exact (equal-distance
-        ties flagged, see parity.compare_flagging_ties); fields to 1e-6 (q 1e-5), because random scenes trap rays between
-        curved faces where the reference's own root tolerance (brentq xtol = 2e-12 absolute) is amplified per bounce.
-    (b) Single interactions: every popped ray of (a) restarted on both sides from identical inputs and traced for
-        three pops: the strict 1e-9 bar on every field."""
+def _fuzz_block(engine, seeds, **fuzz_kw):
+    """Whole paths (ties flagged, loose fields) + restarted single interactions (strict) for a range of fuzz seeds;
+    returns (pops, restarted rays, flagged roots, rays compared)."""
     import optable_b200 as ob
     from optable_b200.flatten import FlatScene, pack_rays, trace_cap
     from oracle import oracle as O
@@ -63,8 +57,8 @@ def test_fuzz_scenes_cuda_equals_oracle(engine, block):
     from tests import scenes
 
     pops = flagged = rays = restarted = 0
-    for seed in range(1000 + 50 * block, 1050 + 50 * block):
-        sc = scenes.fuzz(ob, seed, n_rays=64)
+    for seed in seeds:
+        sc = scenes.fuzz(ob, seed, n_rays=64, **fuzz_kw)
         flat = FlatScene(sc.components, sc.monitors)
         arrs, fam_ids, unit = pack_rays(sc.rays)
         params = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
@@ -87,7 +81,29 @@ def test_fuzz_scenes_cuda_equals_oracle(engine, block):
         restarted += len(batch["ox"])
         flagged += len(ties1)
         rays += len(batch["ox"])
+    return pops, restarted, flagged, rays
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_fuzz_scenes_cuda_equals_oracle(engine, block):
+    """300 random scenes over the component zoo (tests/scenes.fuzz, 64 rays each, built with this package's
+    classes), CUDA path through the C ABI against the C oracle.
+    (a) Whole paths (up to 60 pops, splitting): winning leaf, pop numbering and segment counts exact (equal-distance
+        ties flagged, see parity.compare_flagging_ties); fields to 1e-6 (q 1e-5), because random scenes trap rays between
+        curved faces where the reference's own root tolerance (brentq xtol = 2e-12 absolute) is amplified per bounce.
+    (b) Single interactions: every popped ray of (a) restarted on both sides from identical inputs and traced for
+        three pops: the strict 1e-9 bar on every field."""
+    pops, restarted, flagged, rays = _fuzz_block(engine, range(1000 + 50 * block, 1050 + 50 * block))
     # equal-distance ties between coplanar overlapping apertures: a few per 1e4 rays
+    assert pops > 5000 and restarted > 4000 and flagged <= 2e-3 * rays, (flagged, rays)
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_fuzz_scenes_whole_zoo_cuda_equals_oracle(engine, block):
+    """The same two comparisons over the extended zoo (tests/scenes.fuzz(extended=True): + MMA, MirrorPair,
+    MirrorPrism, TriangularPrism with its built-in caps, DovePrism polygons, the exact-spherical asphere, bare
+    refractive faces)."""
+    pops, restarted, flagged, rays = _fuzz_block(engine, range(50000 + 50 * block, 50050 + 50 * block), extended=True)
     assert pops > 5000 and restarted > 4000 and flagged <= 2e-3 * rays, (flagged, rays)
 
 
