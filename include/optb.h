@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OPTB_ABI_VERSION 6
+#define OPTB_ABI_VERSION 7
 
 /* ---- scene node table ------------------------------------------------------
  * The component tree (OpticalTable.components, groups nested to any depth) is
@@ -117,8 +117,12 @@ enum {
 enum { OPTB_POLY_HEADER = 19 };
 
 /* material table (optable/material.py): kind 0 = constant n (f[0]),
- * kind 1 = Sellmeier-3 (f[0..2] = B, f[3..5] = C in um^2)                  :93-120  */
-enum { OPTB_MAT_CONST = 0, OPTB_MAT_SELLMEIER = 1, OPTB_MF_STRIDE = 8 };
+ * kind 1 = Sellmeier-3 (f[0..2] = B, f[3..5] = C in um^2)                  :93-120,
+ * kind 2 = per-wavelength table for Material(n=<any Python callable>)      :4-21: the host evaluates the callable
+ *          once per distinct wavelength of the batch; f[0] = offset (in doubles) into the aux pool,
+ *          f[1] = number of entries; entries are (wavelength_in_metres, n) pairs sorted by wavelength. The device
+ *          looks the ray's wavelength*unit up by exact match; a miss raises OPTB_ST_LUT_MISS.                  */
+enum { OPTB_MAT_CONST = 0, OPTB_MAT_SELLMEIER = 1, OPTB_MAT_LUT = 2, OPTB_MF_STRIDE = 8 };
 
 /* monitor table (optable/monitor.py:5-13): c[3], Tinv[9], w/2, h/2, then the LAB-frame
  * tangent_Y / tangent_Z (columns 1,2 of transform_matrix). Monitor.get_yList dots the
@@ -188,7 +192,27 @@ typedef struct optb_params {
                              initial count + max_trace_num * rays per family). Counts are still kept, but the
                              scene is traced on the parallel path instead of the family-serial one. If a cap
                              binds anyway, OPTB_ST_CAP_ORDER is raised.                                  */
+  int32_t flag_ambiguity; /* 1: evaluate the ambiguity mask of SURVEY A.9 at every pop (OPTB_AMB_* bits OR-ed per
+                             initial ray into optb_result.root_flags, flagged roots counted in OPTB_C_FLAGGED).
+                             A diagnostics mode: it runs the general kernel variant.                        */
+  int32_t reserved;
 } optb_params;
+
+/* Ambiguity bits (the "stated epsilon" of the parity bar): set for an initial ray when, at some pop,
+ * a decision of the reference hinges on less than the stated margin, so that hit index / bounce count of that
+ * ray are excluded from bit-exact comparison.                                                               */
+enum {
+  OPTB_AMB_TIE = 1,       /* the two closest candidate surfaces are hit within 1e-9 relative of each other   */
+  OPTB_AMB_APERTURE = 2,  /* a hit or near-hit lies within 1e-9 * scale of an aperture edge (r - radius, |y| - w/2,
+                             |z| - h/2, cap x limits, cylinder theta / z limits, polygon edge)                 */
+  OPTB_AMB_GRAZING = 4,   /* |d.n| < 1e-6 at the interaction                                                  */
+  OPTB_AMB_TIR = 8,       /* |sin_t - 1| < 1e-9 (transmission vs total internal reflection)                    */
+  OPTB_AMB_EPS = 16,      /* a candidate t within 1e-11 of the 1e-9 self-intersection guard, or within 1e-9
+                             relative of the ray's length limit                                               */
+  OPTB_AMB_SCAN = 32,     /* curved leaf: a sign-scan sample with |f| < 1e-12, or the bracket within 1e-9 of the
+                             t = 100 clip                                                                      */
+  OPTB_AMB_SLAB = 64      /* a box test with | |d_axis| - 1e-8 | < 1e-10, or passed/failed by less than 1e-11   */
+};
 
 /* ---- results ---------------------------------------------------------------
  * Segments: one per pop (optical_table.py:115-134): the truncated parent on a
@@ -224,6 +248,12 @@ typedef struct optb_result {
   double* hit_t;
   double* hit_dx; double* hit_dy; double* hit_dz; /* lab direction of the segment    */
   double* hit_q_re; double* hit_q_im;
+  uint64_t* hit_key;       /* optional packed row key: root << 32 | monitor << 24 | pop (needs max_trace_num <= 2^24
+                              and <= 256 monitors). Numeric order of the key = (root, monitor, pop) = the order
+                              Monitor.record fills _data_raw when the initial rays are traced one after another.
+                              8 B instead of the 12 B of hit_monitor + hit_root + hit_pop (which may then be NULL,
+                              hit_monitor included)                                                        */
+  uint32_t* root_flags;    /* [rays.n] OPTB_AMB_* bits per initial ray (params.flag_ambiguity = 1); may be NULL */
   /* histograms: int64 [n_monitors][30] over local y in +-w/2, [n_monitors][30][30] over (y,z) */
   int64_t* hist_y;
   int64_t* hist_yz;
@@ -243,15 +273,20 @@ enum {
   OPTB_C_STATUS = 5,       /* bit flags OPTB_ST_*                                     */
   OPTB_C_GENERATIONS = 6,  /* wavefront generations executed                          */
   OPTB_C_LAUNCHES = 7,     /* kernels launched by this call                           */
-  OPTB_C_COUNT = 8
+  OPTB_C_TESTS_CURVED = 8, /* the part of OPTB_C_TESTS that ran the curved branch (local box + sign scan) */
+  OPTB_C_BOX_TESTS = 9,    /* lab-frame bounding-box tests performed                  */
+  OPTB_C_FLAGGED = 10,     /* initial rays with any OPTB_AMB_* bit (params.flag_ambiguity) */
+  OPTB_C_RESERVED = 11,
+  OPTB_C_COUNT = 12
 };
 
 enum {
   OPTB_ST_SEG_OVERFLOW = 1,  /* seg_capacity too small: counts are right, rows beyond capacity dropped */
   OPTB_ST_HIT_OVERFLOW = 2,
   OPTB_ST_WORK_OVERFLOW = 4, /* workspace too small for the live ray set                */
-  OPTB_ST_CAP_ORDER = 8      /* an interact cap bound while its family had concurrent rays:
+  OPTB_ST_CAP_ORDER = 8,     /* an interact cap bound while its family had concurrent rays:
                                 reference result depends on sequential order          */
+  OPTB_ST_LUT_MISS = 16      /* a ray's wavelength is missing from a material's per-wavelength table */
 };
 
 /* ---- entry points ---------------------------------------------------------- */

@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes and constants against the compiled library."""
 import ctypes as C
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # geometry kinds
 G_GROUP, G_CIRCLE, G_RECT, G_SPHERE, G_ASPHERE, G_CYL, G_POLY2D, G_POLY3D, G_CSG = range(9)
@@ -16,15 +16,17 @@ NI_STRIDE = 12
 NF_AABB, NF_ORIGIN, NF_TINV, NF_T, NF_P = 0, 6, 9, 18, 27
 NF_REFL, NF_TRANS, NF_FOCAL, NF_ROC, NF_CAPMAX, NF_STRIDE = 35, 36, 37, 38, 39, 40
 POLY_HEADER = 19
-MAT_CONST, MAT_SELLMEIER, MF_STRIDE = 0, 1, 8
+MAT_CONST, MAT_SELLMEIER, MAT_LUT, MF_STRIDE = 0, 1, 2, 8
 MON_ORIGIN, MON_TINV, MON_HW, MON_HH, MON_TY, MON_TZ, MON_ORTHO, MON_STRIDE = 0, 3, 12, 13, 14, 17, 20, 24
 HIST_BINS = 30
 
 RF_ALIVE, RF_HASQ = 1, 2
 
-(C_SEGMENTS, C_INTERACTIONS, C_HITS, C_TESTS, C_DROPPED, C_STATUS, C_GENERATIONS, C_LAUNCHES) = range(8)
-C_COUNT = 8
-ST_SEG_OVERFLOW, ST_HIT_OVERFLOW, ST_WORK_OVERFLOW, ST_CAP_ORDER = 1, 2, 4, 8
+(C_SEGMENTS, C_INTERACTIONS, C_HITS, C_TESTS, C_DROPPED, C_STATUS, C_GENERATIONS, C_LAUNCHES, C_TESTS_CURVED,
+ C_BOX_TESTS, C_FLAGGED, C_RESERVED) = range(12)
+C_COUNT = 12
+ST_SEG_OVERFLOW, ST_HIT_OVERFLOW, ST_WORK_OVERFLOW, ST_CAP_ORDER, ST_LUT_MISS = 1, 2, 4, 8, 16
+AMB_TIE, AMB_APERTURE, AMB_GRAZING, AMB_TIR, AMB_EPS, AMB_SCAN, AMB_SLAB = 1, 2, 4, 8, 16, 32, 64
 
 _vp = C.c_void_p
 
@@ -52,6 +54,7 @@ class Params(C.Structure):
         ("max_trace_num", C.c_int64), ("unit", C.c_double),
         ("record_segments", C.c_int32), ("record_hits", C.c_int32), ("record_hist", C.c_int32),
         ("chain_len", C.c_int32), ("n_families", C.c_int32), ("caps_slack", C.c_int32),
+        ("flag_ambiguity", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -69,6 +72,7 @@ class Result(C.Structure):
     _fields_ = (
         [("seg_capacity", C.c_int64), ("hit_capacity", C.c_int64)]
         + [(k, _vp) for k in SEG_F64 + SEG_U32 + SEG_I32 + HIT_I32 + HIT_U32 + HIT_F64]
+        + [("hit_key", _vp), ("root_flags", _vp)]
         + [("hist_y", _vp), ("hist_yz", _vp), ("cap_counts", _vp), ("counters", _vp)]
     )
 

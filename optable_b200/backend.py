@@ -171,7 +171,8 @@ class Engine:
 
     SLAB_LIMIT = 4 << 20
 
-    def alloc_result(self, scene: Scene, seg_capacity, hit_capacity, n_families, cap_counts=None, slab=False):
+    def alloc_result(self, scene: Scene, seg_capacity, hit_capacity, n_families, cap_counts=None, slab=False,
+                     hit_columns=None):
         """Device buffers for one trace + the optb_result that points at them. With `slab`, small results are
         carved out of ONE zeroed buffer (returned as `result._slab`, layout in `result._layout`) so that the
         whole result comes back with a single device-to-host copy."""
@@ -180,7 +181,12 @@ class Engine:
         dt = _result_fields(torch)
         nm = max(scene.flat.n_monitors, 1)
         spec = [(k, dt[k], (int(seg_capacity),)) for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32]
-        spec += [(k, dt[k], (int(hit_capacity),)) for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64]
+        # `hit_columns`: the monitor-row columns the caller wants (default: all but the packed key); the others stay
+        # NULL in the result struct: neither allocated nor written
+        want = set(A.HIT_I32 + A.HIT_U32 + A.HIT_F64) if hit_columns is None else set(hit_columns)
+        spec += [(k, dt[k], (int(hit_capacity),)) for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64 if k in want]
+        if "hit_key" in want:
+            spec += [("hit_key", torch.int64, (int(hit_capacity),))]
         spec += [("hist_y", torch.int64, (nm, A.HIST_BINS)), ("hist_yz", torch.int64, (nm, A.HIST_BINS, A.HIST_BINS)),
                  ("cap_counts", torch.int32, (max(scene.flat.n_capslots, 1), max(int(n_families), 1))),
                  ("counters", torch.int64, (A.C_COUNT,))]
@@ -215,11 +221,12 @@ class Engine:
 
     @staticmethod
     def make_params(max_trace_num=2000, unit=1e-2, record_segments=True, record_hits=True, record_hist=False,
-                    chain_len=0, n_families=1, caps_slack=0):
+                    chain_len=0, n_families=1, caps_slack=0, flag_ambiguity=False):
         p = A.Params()
         p.max_trace_num, p.unit = int(max_trace_num), float(unit)
         p.record_segments, p.record_hits, p.record_hist = int(record_segments), int(record_hits), int(record_hist)
         p.chain_len, p.n_families, p.caps_slack = int(chain_len), int(n_families), int(caps_slack)
+        p.flag_ambiguity = int(bool(flag_ambiguity))
         return p
 
     def trace_device(self, scene: Scene, rays_t, params: A.Params, result: A.Result, max_live=None, stream=None):
@@ -268,9 +275,14 @@ class Engine:
         nhit = min(pops_max * flat.n_monitors, 8 * n + 1024) if record_hits else 0
         prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families, slack)
         np_dt = {torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32}
-        for attempt in range(2):
+        # The live ray set of a splitting scene is not known in advance either: a root pops at most max_trace_num rays
+        # and every pop queues at most two, so 2 n max_trace_num live rays always suffice; grow towards that bound.
+        live_bound = max(2 * n * max(int(max_trace_num), 1), 1024)
+        live = max_live
+        retried_rows = False
+        while True:
             res, t = self.alloc_result(scene, nseg, nhit, n_families, caps0, slab=True)
-            self.trace_device(scene, rays_t, prm, res, max_live)
+            self.trace_device(scene, rays_t, prm, res, live)
             host = None
             if res._slab is not None:  # everything in one copy (synchronises)
                 raw = res._slab.cpu().numpy()
@@ -279,10 +291,15 @@ class Engine:
             else:
                 cnt = t["counters"].cpu().numpy()
             st = int(cnt[A.C_STATUS])
-            if not st & (A.ST_SEG_OVERFLOW | A.ST_HIT_OVERFLOW):
-                break
             if st & A.ST_WORK_OVERFLOW:
-                self._raise_status(cnt)
+                cur = live if live is not None else max(4 * n, 1024)
+                if cur >= live_bound:
+                    self._raise_status(cnt)
+                live = min(4 * cur, live_bound)
+                continue
+            if not st & (A.ST_SEG_OVERFLOW | A.ST_HIT_OVERFLOW) or retried_rows:
+                break
+            retried_rows = True
             nseg = int(cnt[A.C_SEGMENTS]) if record_segments else 0
             nhit = int(cnt[A.C_HITS]) if record_hits else 0
         self._raise_status(cnt)

@@ -104,16 +104,16 @@ class DeviceTrace:
     result buffers and workspace are allocated once; `run` only enqueues kernels."""
 
     def __init__(self, engine, flat, n_rays, hit_capacity, seg_capacity=0, hit_columns=HIT_COLUMNS_ALL,
-                 max_trace_num=2000, unit=1e-2, record_hist=False, chain_len=0):
+                 max_trace_num=2000, unit=1e-2, record_hist=False, chain_len=0, flag_ambiguity=False):
         import torch
 
         self.engine, self.flat, self.torch = engine, flat, torch
         self.scene = engine.upload(flat)
-        self.res, self.t = engine.alloc_result(self.scene, seg_capacity, hit_capacity, n_rays)
-        for k in HIT_COLUMNS_ALL:
-            if k not in hit_columns and k != "hit_monitor":
-                setattr(self.res, k, None)
-                self.t.pop(k)
+        self.res, self.t = engine.alloc_result(self.scene, seg_capacity, hit_capacity, n_rays,
+                                               hit_columns=tuple(hit_columns) + (() if "hit_key" in hit_columns else ("hit_monitor",)))
+        if flag_ambiguity:
+            self.t["root_flags"] = torch.zeros(max(int(n_rays), 1), dtype=torch.int32, device=f"cuda:{engine.device}")
+            self.res.root_flags = self.t["root_flags"].data_ptr()
         slack = 0
         if flat.n_capslots:
             # a bundle ray is its own `_id` family starting from zero counts: a cap can only bind if it is
@@ -123,8 +123,8 @@ class DeviceTrace:
                 raise NotImplementedError("bundle traces need max_interact_count >= max_trace_num on every capped component")
             slack = 1
         self.prm = engine.make_params(max_trace_num, unit, seg_capacity > 0, hit_capacity > 0, record_hist, chain_len,
-                                      n_rays, slack)
-        self.hit_columns = tuple(k for k in HIT_COLUMNS_ALL if k in self.t)
+                                      n_rays, slack, flag_ambiguity)
+        self.hit_columns = tuple(k for k in HIT_COLUMNS_ALL + ("hit_key",) if k in self.t)
 
     def run(self, rays_t, max_live=None):
         if self.flat.n_capslots:

@@ -29,6 +29,9 @@ namespace {
 #ifndef OPTB_MIN_BLOCKS
 #define OPTB_MIN_BLOCKS 4
 #endif
+#ifndef OPTB_LAZY_BOXES
+#define OPTB_LAZY_BOXES 0   // measured on B200 (r2a): the lab boxes cull 30-35 % of the leaf tests of lens groups; testing every leaf first costs more (c3 8.2 -> 9.0 ms)
+#endif
 constexpr int kBlock = 128;
 constexpr int kTile = 2048;  // children-scan tile (entries per block)
 constexpr int kScanBlock = 256;
@@ -138,12 +141,13 @@ OPTB_DEV void load_ray(const TraceArgs& a, long long i, Ray& r, bool& solo, uint
   }
 }
 
-OPTB_DEV void store_child(const RayBuf& c, long long j, const Ray& parent, const Children& ch, int k, uint32_t pop_base,
-                           int leaf) {
-  c.f[0][j] = ch.ox; c.f[1][j] = ch.oy; c.f[2][j] = ch.oz;
-  c.f[3][j] = ch.dx[k]; c.f[4][j] = ch.dy[k]; c.f[5][j] = ch.dz[k];
-  c.f[6][j] = ch.I[k]; c.f[7][j] = parent.wl; c.f[8][j] = ch.qre[k]; c.f[9][j] = ch.qim[k];
-  c.f[10][j] = ch.pl; c.f[11][j] = ch.nmed[k]; c.f[12][j] = parent.len;
+OPTB_DEV void store_child(const RayBuf& c, long long j, const Ray& parent, double ox, double oy, double oz, double pl,
+                           double dx, double dy, double dz, double I, double qre, double qim, double nmed, int k,
+                           uint32_t pop_base, int leaf) {
+  c.f[0][j] = ox; c.f[1][j] = oy; c.f[2][j] = oz;
+  c.f[3][j] = dx; c.f[4][j] = dy; c.f[5][j] = dz;
+  c.f[6][j] = I; c.f[7][j] = parent.wl; c.f[8][j] = qre; c.f[9][j] = qim;
+  c.f[10][j] = pl; c.f[11][j] = nmed; c.f[12][j] = parent.len;
   c.flags[j] = parent.flags; c.root[j] = parent.root; c.pop[j] = pop_base; c.family[j] = parent.family;
   c.key[j] = ((uint32_t)leaf << 1) | (uint32_t)k;
 }
@@ -177,12 +181,31 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
   }
   for (int m = 0; m < sv.n_mons; m++) {
     const double* mf = sv.mon + m * OPTB_MON_STRIDE;
-    double ox, oy, oz, dx, dy, dz;
-    to_local(mf + OPTB_MON_ORIGIN, mf + OPTB_MON_TINV, r, mf[OPTB_MON_ORTHO] != 0.0, ox, oy, oz, dx, dy, dz);
+    // Monitor.record (monitor.py:183-193) = to-local + planar hit with t <= length, in stages like intersect_planar:
+    // the x row of Tinv decides "in front, not parallel" and (orthonormal frame) gives t; most segments end here
+    const double* c = mf + OPTB_MON_ORIGIN;
+    const double* Ti = mf + OPTB_MON_TINV;
+    const double vx = r.ox - c[0], vy = r.oy - c[1], vz = r.oz - c[2];
+    const double ox = dot3(Ti[0], Ti[1], Ti[2], vx, vy, vz);
+    double dx = dot3(Ti[0], Ti[1], Ti[2], r.dx, r.dy, r.dz);
     if (!((ox < 0.0 && dx > 0.0) || (ox > 0.0 && dx < 0.0))) continue;  // t = -ox/dx >= 1e-9 needs opposite signs
-    double t = -ox / dx;
+    double dy, dz;
+    const bool ortho = mf[OPTB_MON_ORTHO] != 0.0;
+    if (!ortho) {
+      dy = dot3(Ti[3], Ti[4], Ti[5], r.dx, r.dy, r.dz);
+      dz = dot3(Ti[6], Ti[7], Ti[8], r.dx, r.dy, r.dz);
+      const double rn = rsqrt(dot3(dx, dy, dz, dx, dy, dz));
+      dx *= rn; dy *= rn; dz *= rn;
+    }
+    const double t = -ox / dx;
     if (!(t >= 1e-9) || t > seg_len) continue;
-    double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+    if (ortho) {
+      dy = dot3(Ti[3], Ti[4], Ti[5], r.dx, r.dy, r.dz);
+      dz = dot3(Ti[6], Ti[7], Ti[8], r.dx, r.dy, r.dz);
+    }
+    const double oy = dot3(Ti[3], Ti[4], Ti[5], vx, vy, vz);
+    const double oz = dot3(Ti[6], Ti[7], Ti[8], vx, vy, vz);
+    const double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
     if (!(fabs(Py) <= mf[OPTB_MON_HW] && fabs(Pz) <= mf[OPTB_MON_HH])) continue;
     if (a.rec_hist) {
       double y = dot3(Px, Py, Pz, mf[OPTB_MON_TY], mf[OPTB_MON_TY + 1], mf[OPTB_MON_TY + 2]);
@@ -205,7 +228,8 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
       unsigned long long j = warp_alloc(&a.counters[OPTB_C_HITS]);
       if (j < (unsigned long long)a.out.hit_capacity) {
         const optb_result& o = a.out;
-        o.hit_monitor[j] = m;
+        if (o.hit_monitor) o.hit_monitor[j] = m;
+        if (o.hit_key) o.hit_key[j] = ((unsigned long long)r.root << 32) | ((unsigned long long)m << 24) | (unsigned long long)r.pop;
         if (o.hit_root) o.hit_root[j] = r.root;
         if (o.hit_pop) o.hit_pop[j] = r.pop;
         if (o.hit_px) o.hit_px[j] = Px;
@@ -235,15 +259,22 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
 template <bool ASPH>
 struct HitSearch {
   const TraceArgs& a; const SceneView& sv; const Ray& ray; bool solo;
-  double best_t; int best_node; unsigned int& tests;
+  double best_t; int best_node; unsigned int* cnt;  // cnt: this thread's {leaf tests, curved tests, box tests} in smem
 
   OPTB_DEV void test_leaf(int i, const int32_t* __restrict__ ni, const double* __restrict__ nf) {
-    double ox, oy, oz, dx, dy, dz;
-    to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
-    tests++;
+    atomicAdd(cnt, 1u);  // shared-memory add without a result: one instruction, no register held across the search
     const int slot = ni[OPTB_NI_CAPSLOT];
     // a capped surface counts every geometric hit, closest or not (optical_component.py:359-362): no early exit
-    double t = intersect_leaf<ASPH>(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len, slot >= 0 ? INFINITY : best_t);
+    const double t_beat = slot >= 0 ? INFINITY : best_t;
+    double t;
+    if (OPTB_STAGED_PLANAR && is_planar_kind(ni[OPTB_NI_GEOM])) {
+      t = intersect_planar(sv, ni, nf, ray, t_beat);
+    } else {
+      if (!is_planar_kind(ni[OPTB_NI_GEOM])) atomicAdd(cnt + kBlock, 1u);
+      double ox, oy, oz, dx, dy, dz;
+      to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
+      t = intersect_leaf<ASPH>(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len, t_beat);
+    }
     if (!(t >= 0.0)) return;
     if (slot >= 0) {  // should_interact / increase_interact_count :136-149
       int32_t* cnt = a.out.cap_counts + (long long)slot * a.n_families + ray.family;
@@ -258,19 +289,29 @@ struct HitSearch {
   }
 };
 
-template <bool BOXES, bool ASPH>
+// BOXES: 0 = the scene has no lab-box test at all (top-level leaves only);
+//        1 = pre-order walk, a failed box test skips the subtree (component_group.py:98-115 as a forward scan);
+//        2 = small scenes (<= 32 nodes, no interact caps): every leaf is tested first and only the WINNER's boxes
+//            (its own and its ancestors') are checked afterwards. A leaf the reference would have culled can only
+//            change the result by winning, and a winner whose box chain fails is struck out together with the
+//            failed subtree and the search repeated: the outcome is the reference's, at two box tests per pop
+//            instead of one per node (a lens group of 2-3 faces: 4-8 per pop).
+template <int BOXES, bool ASPH>
 OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
-                          double& best_t, int& best_node, unsigned int& tests) {
+                          double& best_t, int& best_node, unsigned int* cnt) {
   best_t = INFINITY; best_node = -1;
   const bool no_work = !(ray.flags & OPTB_RF_ALIVE);  // optical_component.py:349-350: a dead ray hits nothing
-  HitSearch<ASPH> hs{a, sv, ray, solo, INFINITY, -1, tests};
+  HitSearch<ASPH> hs{a, sv, ray, solo, INFINITY, -1, cnt};
+  unsigned int n_box = 0;
   constexpr int kPark = 4;
   int parked[kPark];
   int n_parked = 0, n_done = 0;
   int i = 0;
   const int n = sv.n_nodes;
-  // BOXES = false: a scene of top-level leaves only has no box test at all (and pays no reciprocals for one)
-  const BoxRay br(ray.ox, ray.oy, ray.oz, BOXES ? ray.dx : 1.0, BOXES ? ray.dy : 1.0, BOXES ? ray.dz : 1.0);
+  // BOXES = 0: a scene of top-level leaves only has no box test at all (and pays no reciprocals for one)
+  // (BOXES = 2 builds it when the winner is verified: 18 registers less during the leaf tests)
+  const BoxRay br(ray.ox, ray.oy, ray.oz, BOXES == 1 ? ray.dx : 1.0, BOXES == 1 ? ray.dy : 1.0, BOXES == 1 ? ray.dz : 1.0);
+  unsigned excl = 0u;  // BOXES == 2: nodes whose subtree the ray is known to miss by a box test
   // Warp-synchronous "walk, then test": in every round each lane walks boxes until it holds a leaf (or runs out of
   // nodes and takes a parked asphere), then the lanes that called in together meet again at the vote and run the
   // one, long leaf test side by side. Without the explicit vote the compiler is free to fold the test into the
@@ -278,14 +319,18 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   // (measured: 3x on the 7,689-leaf scene). One test_leaf call site also keeps the kernel's code size down.
   const unsigned group = __activemask();
   bool searching = !no_work;
-  // (scenes without box tests yield a leaf per walk step: all lanes are in lock-step anyway, no vote needed)
-  while (BOXES ? __any_sync(group, searching) : searching) {
+  // (scenes without box walk yield a leaf per walk step: all lanes are in lock-step anyway, no vote needed)
+  while (BOXES == 1 ? __any_sync(group, searching) : searching) {
     int leaf = -1;
     if (searching) {
       while (i < n) {
         const double* tv = sv.trav + i * 8;
         const int2 gs = *reinterpret_cast<const int2*>(tv + 6);  // {geometry kind, skip}
-        if (BOXES && *reinterpret_cast<const int*>(tv + 7) && !slab_hit(br, tv)) { i = gs.y; continue; }
+        if (BOXES == 1 && *reinterpret_cast<const int*>(tv + 7)) {
+          n_box++;
+          if (!slab_hit(br, tv)) { i = gs.y; continue; }
+        }
+        if (BOXES == 2 && ((excl >> i) & 1u)) { i = gs.y; continue; }
         const int g = gs.x;
         const int cur = i++;
         if (g == OPTB_G_GROUP) continue;
@@ -303,6 +348,24 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
 #pragma unroll
           for (int k = 0; k < kPark; k++) if (k == n_done) leaf = parked[k];
           n_done++;
+        } else if (BOXES == 2 && hs.best_node >= 0) {
+          // every leaf tested: the winner must also pass its own box and those of its ancestors
+          int bad = -1;
+          const BoxRay vr(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz);
+          for (int j = hs.best_node; j >= 0;) {
+            const double* tv = sv.trav + j * 8;
+            const int2 fp = *reinterpret_cast<const int2*>(tv + 7);  // {box-test flag, parent}
+            if (fp.x) { n_box++; if (!slab_hit(vr, tv)) bad = j; }  // keeps the outermost failing node
+            j = fp.y;
+          }
+          if (bad < 0) {
+            searching = false;
+          } else {  // strike the failed subtree out and search again (rare: stale or under-covering boxes)
+            const int end = reinterpret_cast<const int2*>(sv.trav + bad * 8 + 6)->y;
+            excl |= (end >= 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << bad) - 1u);
+            hs.best_t = INFINITY; hs.best_node = -1;
+            i = 0; n_parked = 0; n_done = 0;
+          }
         } else {
           searching = false;
         }
@@ -311,14 +374,19 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
     if (leaf >= 0) hs.test_leaf(leaf, sv.ni + leaf * OPTB_NI_STRIDE, sv.nf + leaf * OPTB_NF_STRIDE);
   }
   best_t = hs.best_t; best_node = hs.best_node;
+  if (BOXES) atomicAdd(cnt + 2 * kBlock, n_box);
 }
 
-template <bool SMEM, bool SERIAL, bool BOXES, bool ASPH>
+// SPLIT = some interaction of the scene can emit two rays (or the caller bounded the in-register chain): the
+// wavefront machinery (child slots, per-root generation ranks) is compiled in. Scenes that cannot split run the
+// whole life of a ray in registers with none of it.
+template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT>
 // Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
 // spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
 // whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
 __global__ void __launch_bounds__(kBlock, (SMEM || ASPH || SERIAL) ? OPTB_MIN_BLOCKS : OPTB_MIN_BLOCKS + 1)
 trace_kernel(const __grid_constant__ TraceArgs a) {
+  constexpr int MAXCH = (SPLIT || SERIAL) ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
   // The closest-hit search only needs a ray's geometry. Its radiometric state (intensity, wavelength, q, path
@@ -326,6 +394,9 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
   __shared__ double s_park[6][kBlock];
   __shared__ double s_icn[3][kBlock];   // index memo: wavelength, n of slot 0, n of slot 1
   __shared__ int s_icm[2][kBlock];      // material index of slot 0 / slot 1
+  __shared__ unsigned int s_cnt[3][kBlock];  // per thread: leaf tests, curved leaf tests, lab-box tests
+  s_cnt[0][threadIdx.x] = 0u; s_cnt[1][threadIdx.x] = 0u; s_cnt[2][threadIdx.x] = 0u;
+  unsigned int* const my_cnt = &s_cnt[0][threadIdx.x];
   s_icn[0][threadIdx.x] = -1.0; s_icm[0][threadIdx.x] = -1; s_icm[1][threadIdx.x] = -1;
   const IndexCache ic{&s_icn[0][threadIdx.x], &s_icn[1][threadIdx.x], &s_icn[2][threadIdx.x], &s_icm[0][threadIdx.x],
                       &s_icm[1][threadIdx.x]};
@@ -352,6 +423,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
   sv.mon = (const double*)(base + a.off.mon);
   sv.aux = (const double*)(base + a.off.aux);
   sv.n_nodes = a.n_nodes; sv.n_mons = a.n_mons;
+  sv.status = &a.counters[OPTB_C_STATUS];
 
   const int per = OPTB_HIST_BINS * (OPTB_HIST_BINS + 1);
   unsigned int* s_hist = (unsigned int*)(smem_raw + (SMEM ? ((a.blob_bytes + 15u) & ~15u) : 0u));
@@ -362,7 +434,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
 
   const long long n_in = a.n_in_dev ? (long long)*a.n_in_dev : a.n_in;
   const int lane = threadIdx.x & 31;
-  unsigned int c_pops = 0, c_inter = 0, c_tests = 0, c_drop = 0, c_hits = 0;  // per thread; widened when reduced
+  unsigned int c_pops = 0, c_inter = 0, c_drop = 0, c_hits = 0;  // per thread; widened when reduced
 
   while (true) {
     unsigned int chunk = 0;
@@ -373,7 +445,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
     if (i >= n_in) continue;
     // Wavefront entries are stored in reference (BFS) order, which the pop numbering needs, but processed in the
     // order of their coherence key: rays that left the same surface the same way sit in the same warp.
-    if (!SERIAL && a.perm) i = a.perm[i];
+    if (SPLIT && !SERIAL && a.perm) i = a.perm[i];
 
     if constexpr (SERIAL) {
       // Work item = one Ray._id family. Its initial rays are traced one after another in input order, each
@@ -396,7 +468,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
           ring_get(a.w, ring + head % a.qcap, ray); head++;
           ray.root = root; ray.family = (int32_t)i; ray.pop = pops++;
           double t; int node;
-          closest_hit<BOXES, ASPH>(a, sv, ray, true, t, node, c_tests);
+          closest_hit<BOXES, ASPH>(a, sv, ray, true, t, node, my_cnt);
           c_pops++;
           const bool hit = node >= 0;
           const int32_t* ni = sv.ni + (hit ? node : 0) * OPTB_NI_STRIDE;
@@ -407,13 +479,17 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
           c_inter++;
           double ox, oy, oz, dx, dy, dz;
           to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
-          Children ch;
-          interact<ASPH>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
+          Children<MAXCH> ch;
+          interact<ASPH, MAXCH>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
           for (int k = 0; k < ch.n; k++) {
             if (tail - head >= a.qcap) { atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_WORK_OVERFLOW); break; }
             Ray c = ray;
-            c.ox = ch.ox; c.oy = ch.oy; c.oz = ch.oz; c.dx = ch.dx[k]; c.dy = ch.dy[k]; c.dz = ch.dz[k];
-            c.I = ch.I[k]; c.qre = ch.qre[k]; c.qim = ch.qim[k]; c.pl = ch.pl; c.n = ch.nmed[k];
+            c.ox = ch.ox; c.oy = ch.oy; c.oz = ch.oz;
+            const bool second = (k == 1);
+            c.dx = second ? ch.dx[MAXCH - 1] : ch.dx[0]; c.dy = second ? ch.dy[MAXCH - 1] : ch.dy[0];
+            c.dz = second ? ch.dz[MAXCH - 1] : ch.dz[0]; c.I = second ? ch.I[MAXCH - 1] : ch.I[0];
+            c.qre = second ? ch.qre[MAXCH - 1] : ch.qre[0]; c.qim = second ? ch.qim[MAXCH - 1] : ch.qim[0];
+            c.n = second ? ch.nmed[MAXCH - 1] : ch.nmed[0]; c.pl = ch.pl;
             ring_put(a.w, ring + tail % a.qcap, c); tail++;
           }
         }
@@ -424,11 +500,12 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
 
     Ray ray; bool solo; uint32_t gcount;
     load_ray(a, i, ray, solo, gcount);
-    const uint32_t pop_base_next = a.gen0 ? 0u : (ray.pop - (uint32_t)(i - a.gen_first[ray.root]) + gcount);
+    if (!SPLIT) solo = true;
+    const uint32_t pop_base_next = (!SPLIT || a.gen0) ? 0u : (ray.pop - (uint32_t)(i - a.gen_first[ray.root]) + gcount);
     int nch = 0;
     int chained = 0;
     int hit_leaf = 0;
-    Children ch;
+    Children<MAXCH> ch;
     ch.n = 0;
     while (true) {
       if ((long long)ray.pop >= a.max_trace) { c_drop++; nch = 0; break; }  // queued but never popped
@@ -437,7 +514,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
         volatile double* pk = &s_park[0][threadIdx.x];
         pk[0 * kBlock] = ray.I; pk[1 * kBlock] = ray.wl; pk[2 * kBlock] = ray.qre;
         pk[3 * kBlock] = ray.qim; pk[4 * kBlock] = ray.pl; pk[5 * kBlock] = ray.n;
-        closest_hit<BOXES, ASPH>(a, sv, ray, solo, t, node, c_tests);
+        closest_hit<BOXES, ASPH>(a, sv, ray, solo, t, node, my_cnt);
         ray.I = pk[0 * kBlock]; ray.wl = pk[1 * kBlock]; ray.qre = pk[2 * kBlock];
         ray.qim = pk[3 * kBlock]; ray.pl = pk[4 * kBlock]; ray.n = pk[5 * kBlock];
       }
@@ -454,9 +531,9 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
       hit_leaf = ni[OPTB_NI_LEAF];
       double ox, oy, oz, dx, dy, dz;
       to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
-      interact<ASPH>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
+      interact<ASPH, MAXCH>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
       nch = ch.n;
-      if (nch == 1 && solo && (a.chain_len == 0 || chained + 1 < a.chain_len)) {
+      if (nch == 1 && solo && (!SPLIT || a.chain_len == 0 || chained + 1 < a.chain_len)) {
         // the root's alive set is this one ray: BFS order is trivially kept, continue in registers
         ray.ox = ch.ox; ray.oy = ch.oy; ray.oz = ch.oz;
         ray.dx = ch.dx[0]; ray.dy = ch.dy[0]; ray.dz = ch.dz[0];
@@ -466,17 +543,23 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
       }
       break;
     }
-    if (a.nchild) {
-      a.nchild[i] = (uint8_t)nch;
-      uint32_t pb = solo ? ray.pop + 1u : pop_base_next;
-      for (int k = 0; k < nch; k++) store_child(a.c, 2 * i + k, ray, ch, k, pb, hit_leaf);
+    if constexpr (SPLIT) {
+      if (a.nchild) {
+        a.nchild[i] = (uint8_t)nch;
+        uint32_t pb = solo ? ray.pop + 1u : pop_base_next;
+        if (nch > 0) store_child(a.c, 2 * i, ray, ch.ox, ch.oy, ch.oz, ch.pl, ch.dx[0], ch.dy[0], ch.dz[0], ch.I[0],
+                                 ch.qre[0], ch.qim[0], ch.nmed[0], 0, pb, hit_leaf);
+        if (nch > 1) store_child(a.c, 2 * i + 1, ray, ch.ox, ch.oy, ch.oz, ch.pl, ch.dx[MAXCH - 1], ch.dy[MAXCH - 1],
+                                 ch.dz[MAXCH - 1], ch.I[MAXCH - 1], ch.qre[MAXCH - 1], ch.qim[MAXCH - 1],
+                                 ch.nmed[MAXCH - 1], 1, pb, hit_leaf);
+      }
     }
   }
 
   // counters: warp reduce then one atomic per warp
-  unsigned long long v[5] = {c_pops, c_inter, c_tests, c_drop, c_hits};
+  unsigned long long v[7] = {c_pops, c_inter, my_cnt[0], c_drop, c_hits, my_cnt[kBlock], my_cnt[2 * kBlock]};
 #pragma unroll
-  for (int k = 0; k < 5; k++) {
+  for (int k = 0; k < 7; k++) {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], s);
   }
@@ -486,6 +569,8 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
     if (v[2]) atomicAdd(&a.counters[OPTB_C_TESTS], v[2]);
     if (v[3]) atomicAdd(&a.counters[OPTB_C_DROPPED], v[3]);
     if (!a.rec_hit && v[4]) atomicAdd(&a.counters[OPTB_C_HITS], v[4]);
+    if (v[5]) atomicAdd(&a.counters[OPTB_C_TESTS_CURVED], v[5]);
+    if (v[6]) atomicAdd(&a.counters[OPTB_C_BOX_TESTS], v[6]);
   }
   if (a.hist_smem) {
     __syncthreads();
@@ -665,13 +750,18 @@ struct optb_ctx {
   // Retired scene blobs, kept for the next upload: cudaMalloc/cudaFree cost milliseconds each (and cudaFree
   // synchronises the device), which is most of the latency of a small trace that re-uploads its scene per call.
   struct { unsigned char* p; size_t cap; } pool[8];
+  // live-ray budget per initial ray that the last splitting optb_trace_host call needed (its grow loop starts there)
+  int64_t live_per_ray_hint;
 };
 
 struct optb_scene {
   unsigned char* d_blob; size_t blob_cap; uint32_t blob_bytes; SceneOff off;
   int n_nodes, n_leaves, n_mats, n_mons, n_caps; long long n_aux;
-  int max_children; int has_boxes; int has_asph;
+  int max_children; int has_boxes; int has_asph; int lazy_boxes;
   bool in_smem; bool hist_smem; uint32_t smem_bytes;
+  // recorded on the stream of every trace that reads the blob: releasing the scene waits for this event only,
+  // not for the whole device (other streams, NCCL and unrelated kernels keep running)
+  cudaEvent_t last_use; bool used;
 };
 
 static int fail(optb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -694,13 +784,18 @@ extern "C" int optb_ctx_create(int device, optb_ctx** out) {
   if (!ctx) return -3;
   memset(ctx, 0, sizeof *ctx);
   ctx->device = device;
-  cudaSetDevice(device);
-  cudaDeviceProp p;
-  cudaGetDeviceProperties(&p, device);
-  ctx->sm_count = p.multiProcessorCount;
-  ctx->smem_optin = p.sharedMemPerBlockOptin;
-  cudaMallocHost((void**)&ctx->h_counters, sizeof(unsigned long long) * OPTB_C_COUNT);
-  cudaMallocHost((void**)&ctx->h_hdr, sizeof(Header));
+  int sm = 0, optin = 0;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_counters, sizeof(unsigned long long) * OPTB_C_COUNT) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_hdr, sizeof(Header)) != cudaSuccess) {
+    cudaGetLastError();
+    optb_ctx_destroy(ctx);
+    return -10;
+  }
+  ctx->sm_count = sm;
+  ctx->smem_optin = (size_t)optin;
   *out = ctx;
   return 0;
 }
@@ -778,11 +873,19 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   if (d->n_nodes) {
     memcpy(host.data() + s->off.nf, d->node_f, b_nf);
     memcpy(host.data() + s->off.ni, d->node_i, b_ni);
+    // parent of every node, from the skip pointers (pre-order: the innermost open group that still covers i)
+    std::vector<int32_t> parent(d->n_nodes, -1), open;
+    for (int i = 0; i < d->n_nodes; i++) {
+      const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
+      while (!open.empty() && d->node_i[(size_t)open.back() * OPTB_NI_STRIDE + OPTB_NI_SKIP] <= i) open.pop_back();
+      parent[i] = open.empty() ? -1 : open.back();
+      if (ni[OPTB_NI_GEOM] == OPTB_G_GROUP) open.push_back(i);
+    }
     for (int i = 0; i < d->n_nodes; i++) {  // compact traversal records
       unsigned char* tv = host.data() + s->off.trav + (size_t)i * 64;
       const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
       memcpy(tv, d->node_f + (size_t)i * OPTB_NF_STRIDE + OPTB_NF_AABB, 48);
-      const int32_t pack[4] = {ni[OPTB_NI_GEOM], ni[OPTB_NI_SKIP], ni[OPTB_NI_AABB], 0};
+      const int32_t pack[4] = {ni[OPTB_NI_GEOM], ni[OPTB_NI_SKIP], ni[OPTB_NI_AABB], parent[i]};
       memcpy(tv + 48, pack, 16);
     }
   }
@@ -813,6 +916,10 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   size_t used = s->in_smem ? o : 0;
   s->hist_smem = (hist_bytes > 0 && used + hist_bytes <= std::min<size_t>(budget, used + 65536));
   s->smem_bytes = (uint32_t)(used + (s->hist_smem ? hist_bytes : 0));
+  // winner-verified box tests (closest_hit BOXES = 2): the struck-out set is one 32-bit mask, interact caps count
+  // every geometric hit of a leaf whose boxes pass (so they need the culling walk), and only shared-memory scenes
+  // test leaves cheaply enough for "test all, verify one" to win
+  s->lazy_boxes = (OPTB_LAZY_BOXES && s->in_smem && s->has_boxes && d->n_capslots == 0 && d->n_nodes <= 32) ? 1 : 0;
   cudaError_t e = cudaSuccess;
   int pick = -1;  // smallest retired blob that is large enough
   for (int k = 0; k < 8; k++)
@@ -826,6 +933,7 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
     if (e != cudaSuccess) { delete s; return fail(ctx, -10, "cudaMalloc(scene)", e); }
   }
   e = cudaMemcpy(s->d_blob, host.data(), o, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->last_use, cudaEventDisableTiming);
   if (e != cudaSuccess) { cudaFree(s->d_blob); delete s; return fail(ctx, -10, "cudaMemcpy(scene)", e); }
   *out = s;
   return 0;
@@ -838,13 +946,14 @@ extern "C" int optb_scene_destroy(optb_ctx* ctx, optb_scene* s) {
     int slot = -1;
     if (ctx && s->blob_cap <= ((size_t)64 << 20))
       for (int k = 0; k < 8 && slot < 0; k++) if (!ctx->pool[k].p) slot = k;
+    if (s->used) cudaEventSynchronize(s->last_use);  // no kernel may still be reading the blob
     if (slot >= 0) {
-      cudaDeviceSynchronize();  // what cudaFree would have done: no kernel may still be reading the blob
       ctx->pool[slot].p = s->d_blob; ctx->pool[slot].cap = s->blob_cap;
     } else {
       cudaFree(s->d_blob);
     }
   }
+  if (s->last_use) cudaEventDestroy(s->last_use);
   delete s;
   return 0;
 }
@@ -938,8 +1047,15 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   cudaSetDevice(ctx->device);
   if (!out->counters) return fail(ctx, -7, "result.counters is required");
   if (rays->n >= 0xffffffffll) return fail(ctx, -7, "at most 2^32-1 rays per call");
-  if (prm->record_hits && out->hit_capacity > 0 && !out->hit_monitor) return fail(ctx, -7, "record_hits needs hit_monitor");
+  if (prm->record_hits && out->hit_capacity > 0 && !out->hit_monitor && !out->hit_key) return fail(ctx, -7, "record_hits needs hit_monitor or hit_key");
+  if (prm->record_hits && out->hit_key && (prm->max_trace_num > (1ll << 24) || scene->n_mons > 256))
+    return fail(ctx, -7, "hit_key packs pop into 24 bits and the monitor into 8: max_trace_num <= 2^24 and <= 256 monitors");
+  if (prm->flag_ambiguity) return fail(ctx, -7, "flag_ambiguity: not available in this build");
   if (scene->n_caps > 0 && (!out->cap_counts || prm->n_families < 1)) return fail(ctx, -7, "scene has interact caps: cap_counts/n_families required");
+  // cap_counts is [n_capslots][n_families]; without a family column every initial ray is its own family (column
+  // index = ray index), so the table must have a column per ray
+  if (scene->n_caps > 0 && !rays->family && (long long)prm->n_families < rays->n)
+    return fail(ctx, -7, "scene has interact caps and rays.family is NULL: n_families must be >= rays.n");
   const bool serial = needs_serial(scene, rays, prm);
   const bool split = !serial && needs_wavefront(scene, prm);
   WsLayout L = ws_layout(rays->n, 0, false);
@@ -964,7 +1080,11 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   } else if (split) {
     // find the largest wavefront capacity the given workspace supports
     if (workspace_bytes < (int64_t)ws_layout(rays->n, rays->n, true).total) return fail(ctx, -8, "workspace too small (see optb_workspace_bytes)");
-    long long lo = rays->n, hi = std::max<long long>(rays->n, 1) * 64;
+    // upper end of the search: what the workspace could hold at ~100 B per live ray (far above the real cost of
+    // ~540 B), so the capacity is set by the caller's workspace and never by the size of the batch: one initial ray
+    // through cascaded beam splitters may need thousands of live rays (the reference allows 2000 pops)
+    long long lo = rays->n, hi = std::max<long long>(rays->n, (long long)(workspace_bytes / 100));
+    hi = std::min<long long>(hi, 0x7ffffff0ll);
     while (lo < hi) {
       long long mid = lo + (hi - lo + 1) / 2;
       if ((int64_t)ws_layout(rays->n, mid, true).total <= workspace_bytes) lo = mid; else hi = mid - 1;
@@ -1010,15 +1130,19 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   }
   uint32_t smem = scene->in_smem ? scene->smem_bytes : (a.hist_smem ? scene->smem_bytes : 0);
   using Kern = void (*)(const TraceArgs);
-  // [smem][boxes][aspheres] for the parallel path; the family-serial path keeps one general variant per staging mode
-  static const Kern table[2][2][2] = {
-      {{trace_kernel<false, false, false, false>, trace_kernel<false, false, false, true>},
-       {trace_kernel<false, false, true, false>, trace_kernel<false, false, true, true>}},
-      {{trace_kernel<true, false, false, false>, trace_kernel<true, false, false, true>},
-       {trace_kernel<true, false, true, false>, trace_kernel<true, false, true, true>}}};
-  static const Kern serial_table[2] = {trace_kernel<false, true, true, true>, trace_kernel<true, true, true, true>};
+  // box mode: 0 none, 1 pre-order walk with culling, 2 winner-verified (small shared-memory scenes without caps)
+  const int boxmode = !scene->has_boxes ? 0 : (scene->lazy_boxes ? 2 : 1);
+  // [smem][box mode][aspheres][split] for the parallel path (box mode 2 only exists with the tables in shared
+  // memory); the family-serial path keeps one general variant per staging mode
+#define OPTB_K(S, B, A, P) trace_kernel<S, false, B, A, P>
+#define OPTB_KROW(S, B) {{OPTB_K(S, B, false, false), OPTB_K(S, B, false, true)}, {OPTB_K(S, B, true, false), OPTB_K(S, B, true, true)}}
+  static const Kern table[2][3][2][2] = {{OPTB_KROW(false, 0), OPTB_KROW(false, 1), OPTB_KROW(false, 1)},
+                                         {OPTB_KROW(true, 0), OPTB_KROW(true, 1), OPTB_KROW(true, 2)}};
+#undef OPTB_KROW
+#undef OPTB_K
+  static const Kern serial_table[2] = {trace_kernel<false, true, 1, true, true>, trace_kernel<true, true, 1, true, true>};
   Kern kern = serial ? serial_table[scene->in_smem ? 1 : 0]
-                     : table[scene->in_smem ? 1 : 0][scene->has_boxes ? 1 : 0][scene->has_asph ? 1 : 0];
+                     : table[scene->in_smem ? 1 : 0][boxmode][scene->has_asph ? 1 : 0][split ? 1 : 0];
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
   int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem), "occupancy");
@@ -1041,7 +1165,6 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     a.w = make_raybuf(ws + SL.ring, qcap * n_fam);
     a.fam_shared = 0;
     a.n_in = n_fam;
-    if (!rays->family) a.n_families = (int)std::min<long long>(n_fam, 0x7fffffff);
     void* kargs[] = {(void*)&a};
     int grid = (int)std::min<long long>(full_grid, (n_fam + kBlock - 1) / kBlock);
     CK(cudaLaunchKernel((const void*)kern, dim3(grid), dim3(kBlock), kargs, smem, st), "launch trace_kernel (family-serial)");
@@ -1107,6 +1230,8 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   }
   finish_kernel<<<1, 1, 0, st>>>(a.counters, gens, launches + 1, hdr);
   CK(cudaGetLastError(), "kernel launch");
+  CK(cudaEventRecord(scene->last_use, st), "record scene use");
+  const_cast<optb_scene*>(scene)->used = true;
   return 0;
 }
 
@@ -1118,7 +1243,7 @@ struct ArenaCursor {
 }  // namespace
 
 static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
-                           optb_result* out, int64_t live_factor);
+                           optb_result* out, int64_t live);
 
 // Chunked, three-stream version of optb_trace_host for scenes that cannot split: the host->device copy of chunk
 // c+1, the trace of chunk c and the device->host copy of chunk c-1 overlap (PCIe is full duplex). Rows of chunk c
@@ -1280,23 +1405,32 @@ extern "C" int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const opt
     int rc = trace_host_pipelined(ctx, scene, rays, prm, out);
     if (rc <= 0) return rc;  // 1 = a chunk outgrew its estimated share of the result capacity: one-shot path
   }
-  // The live ray set of a splitting scene is not known in advance: grow the workspace until it fits.
-  for (int64_t factor = 4; factor <= 1024; factor *= 4) {
-    int rc = trace_host_once(ctx, scene, rays, prm, out, factor);
+  // The live ray set of a splitting scene is not known in advance: grow the workspace until it fits. A root pops at
+  // most max_trace_num rays and every pop queues at most two, so 2 n max_trace_num live rays always suffice.
+  const double bound_d = 2.0 * (double)std::max<int64_t>(rays->n, 1) * (double)std::max<int64_t>(prm->max_trace_num, 1);
+  const int64_t bound = bound_d > 4e9 ? (int64_t)4e9 : (int64_t)bound_d;
+  const int64_t per_ray = std::max<int64_t>(4, ctx->live_per_ray_hint);
+  for (int64_t live = std::min<int64_t>(std::max<int64_t>(per_ray * rays->n, 1024), std::max<int64_t>(bound, 1024));;
+       live = std::min<int64_t>(live * 2, bound)) {
+    int rc = trace_host_once(ctx, scene, rays, prm, out, live);
     if (rc) return rc;
-    if (!(ctx->h_counters[OPTB_C_STATUS] & OPTB_ST_WORK_OVERFLOW)) return 0;
+    if (!(ctx->h_counters[OPTB_C_STATUS] & OPTB_ST_WORK_OVERFLOW)) {
+      if (rays->n > 0 && needs_wavefront(scene, prm)) ctx->live_per_ray_hint = (live + rays->n - 1) / rays->n;
+      return 0;
+    }
+    if (live >= bound) break;
   }
-  return fail(ctx, -8, "live ray set exceeds 1024x the batch: workspace overflow");
+  return fail(ctx, -8, "live ray set exceeds 2 * n * max_trace_num: workspace overflow");
 }
 
 static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
-                           optb_result* out, int64_t live_factor) {
+                           optb_result* out, int64_t live) {
   cudaSetDevice(ctx->device);
   const int64_t n = rays->n;
   const bool split = needs_wavefront(scene, prm) || needs_serial(scene, rays, prm);
   const int64_t segcap = prm->record_segments ? out->seg_capacity : 0, hitcap = prm->record_hits ? out->hit_capacity : 0;
-  const int64_t max_live = split ? std::max<int64_t>(live_factor * n, 1024) : 0;
-  const int64_t wsb = needs_serial(scene, rays, prm) ? optb_workspace_bytes(scene, n, 16 * live_factor * std::max<int64_t>(n, 16))
+  const int64_t max_live = split ? std::max<int64_t>(live, n) : 0;
+  const int64_t wsb = needs_serial(scene, rays, prm) ? optb_workspace_bytes(scene, n, 16 * std::max<int64_t>(live, 64))
                                                : (int64_t)ws_layout(n, max_live, split).total;
   const int nfam = std::max(prm->n_families, 1);
   size_t need = 256 * 64 + (size_t)n * (8 * 13 + 8) + (size_t)segcap * (13 * 8 + 16) + (size_t)hitcap * (10 * 8 + 12) +

@@ -11,6 +11,12 @@
 #include "../../include/optb.h"
 
 #define OPTB_DEV __device__ __forceinline__
+#ifndef OPTB_CH_REGS
+#define OPTB_CH_REGS 1   // Children slots written through selects (registers) instead of indexed stores (local memory)
+#endif
+#ifndef OPTB_STAGED_PLANAR
+#define OPTB_STAGED_PLANAR 1  // planar leaves: x row of Tinv first (intersect_planar) instead of a full to_local
+#endif
 // cold, register-hungry code (once per pop) is kept out of line so that the closest-hit loop gets the registers
 // (measured on B200: keeping them inline is 10 % faster than __noinline__ calls; -DOPTB_NOINLINE_COLD flips it)
 #ifdef OPTB_NOINLINE_COLD
@@ -39,6 +45,7 @@ struct SceneView {
   const double* mon;
   const double* aux;
   int n_nodes, n_mons;
+  unsigned long long* status;  // OPTB_C_STATUS word of the call (device memory)
 };
 
 OPTB_DEV double dot3(double ax, double ay, double az, double bx, double by, double bz) {
@@ -303,7 +310,54 @@ OPTB_DEV double sample_t(int i, double a, double b, double step) {
   return i == 9 ? b : fma(fi, step, a);
 }
 
-// intersect_point_local optical_component.py:151-233 for one leaf, local-frame ray. Returns t or -1.
+OPTB_DEV bool is_planar_kind(int g) { return g == OPTB_G_CIRCLE || g == OPTB_G_RECT || g == OPTB_G_POLY2D || g == OPTB_G_CSG; }
+
+// Planar leaves, straight from the lab ray (ray_to_local_coordinates :106-111 + intersect_point_local :165-196 in
+// one, evaluated in stages): the plane is local x = 0, so the x row of Tinv alone decides whether the ray can reach
+// it at all (t = -ox/dx >= 1e-9 needs ox, dx of opposite signs; the sign of dx does not change under the
+// re-normalisation of the direction), and for an orthonormal frame it also gives t itself. The y and z rows are
+// only paid for by rays that get as far as the aperture test. Returns t or -1.
+OPTB_DEV double intersect_planar(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
+                                 const Ray& r, double t_beat) {
+  const double* c = nf + OPTB_NF_ORIGIN;
+  const double* Ti = nf + OPTB_NF_TINV;
+  const double vx = r.ox - c[0], vy = r.oy - c[1], vz = r.oz - c[2];
+  const double ox = dot3(Ti[0], Ti[1], Ti[2], vx, vy, vz);
+  double dx = dot3(Ti[0], Ti[1], Ti[2], r.dx, r.dy, r.dz);
+  if (!((ox < 0.0 && dx > 0.0) || (ox > 0.0 && dx < 0.0))) return -1.0;
+  double dy, dz;
+  const bool ortho = ni[OPTB_NI_ORTHO] != 0;
+  if (!ortho) {
+    dy = dot3(Ti[3], Ti[4], Ti[5], r.dx, r.dy, r.dz);
+    dz = dot3(Ti[6], Ti[7], Ti[8], r.dx, r.dy, r.dz);
+    const double rn = rsqrt(dot3(dx, dy, dz, dx, dy, dz));
+    dx *= rn; dy *= rn; dz *= rn;
+  }
+  const double t = -ox / dx;
+  if (!(t >= 1e-9) || t > r.len || t > t_beat) return -1.0;  // |t|<EPS, t<0, t>length, NaN; or cannot win any more
+  if (ortho) {
+    dy = dot3(Ti[3], Ti[4], Ti[5], r.dx, r.dy, r.dz);
+    dz = dot3(Ti[6], Ti[7], Ti[8], r.dx, r.dy, r.dz);
+  }
+  const double oy = dot3(Ti[3], Ti[4], Ti[5], vx, vy, vz);
+  const double oz = dot3(Ti[6], Ti[7], Ti[8], vx, vy, vz);
+  const double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+  const int g = ni[OPTB_NI_GEOM];
+  const double* p = nf + OPTB_NF_P;
+  bool in;
+  if (g == OPTB_G_CSG) {
+    bool a = planar_within(sv, (int)p[1], p[2], p[3], Px, Py, Pz);
+    bool b = planar_within(sv, (int)p[4], p[5], p[6], Px, Py, Pz);
+    in = ((int)p[0] == 0) ? (a && !b) : (a || b);
+  } else if (g == OPTB_G_POLY2D) {
+    in = poly_within(sv.aux + ni[OPTB_NI_AUX], Px, Py, Pz);
+  } else {
+    in = planar_within(sv, g, p[0], p[1], Px, Py, Pz);
+  }
+  return in ? t : -1.0;
+}
+
+// intersect_point_local optical_component.py:197-233 (curved branch) for one leaf, local-frame ray. Returns t or -1.
 template <bool ASPH>
 OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
                                double ox, double oy, double oz, double dx, double dy, double dz, double len,
@@ -312,10 +366,9 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
   // only ever reports roots inside its bracket [a, b], so a bracket that starts beyond t_beat is skipped whole.
   const int g = ni[OPTB_NI_GEOM];
   const double* p = nf + OPTB_NF_P;
-  if (g == OPTB_G_CIRCLE || g == OPTB_G_RECT || g == OPTB_G_POLY2D || g == OPTB_G_CSG) {
+#if !OPTB_STAGED_PLANAR
+  if (is_planar_kind(g)) {
     // planar branch :165-196: plane x = 0
-    // t = -ox/dx must be >= 1e-9: origin and direction on opposite sides of the plane (also covers dx == 0,
-    // which the reference resolves to a miss or to t = 0 < EPS); decided before paying for the division
     if (!((ox < 0.0 && dx > 0.0) || (ox > 0.0 && dx < 0.0))) return -1.0;
     double t = -ox / dx;
     if (!(t >= 1e-9) || t > len) return -1.0;  // |t|<EPS, t<0, t>length, NaN
@@ -332,6 +385,8 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
     }
     return in ? t : -1.0;
   }
+#endif
+  // (with OPTB_STAGED_PLANAR planar kinds never get here: intersect_planar)
   // curved branch :197-233. Local AABB (Surface.get_bbox_local) -> bracket -> 10-point sign scan -> roots.
   double bb[6];
   if (g == OPTB_G_SPHERE) {
@@ -496,7 +551,22 @@ OPTB_DEV void surf_normal(const SceneView& sv, const int32_t* __restrict__ ni, c
 // Material.n / SellmeierMaterial.sellmeier_n material.py:12-21, 106-120
 OPTB_DEV double material_n(const SceneView& sv, int m, double wl_m) {
   const double* f = sv.matf + m * OPTB_MF_STRIDE;
-  if (sv.matk[m] == OPTB_MAT_CONST) return f[0];
+  const int kind = sv.matk[m];
+  if (kind == OPTB_MAT_CONST) return f[0];
+  if (kind == OPTB_MAT_LUT) {
+    // Material(n=<Python callable>): evaluated by the host once per distinct wavelength of the batch; (wavelength in
+    // metres, n) pairs sorted by wavelength. wavelength * unit is the same IEEE product on both sides: exact match.
+    const double* tab = sv.aux + (long long)f[0];
+    int lo = 0, hi = (int)f[1] - 1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      const double w = tab[2 * mid];
+      if (w == wl_m) return tab[2 * mid + 1];
+      if (w < wl_m) lo = mid + 1; else hi = mid - 1;
+    }
+    atomicOr(sv.status, (unsigned long long)OPTB_ST_LUT_MISS);
+    return NAN;
+  }
   double wl_um = wl_m / 1e-6;
   double w2 = wl_um * wl_um;
   double n2 = 1.0;
@@ -536,12 +606,25 @@ OPTB_DEV void cdiv(double a, double b, double c, double d, double& re, double& i
   }
 }
 
-// What one interaction emits: both children start at the same lab point.
+// What one interaction emits: all children start at the same lab point. N = most children any interaction of the
+// scene can emit (1 for scenes that cannot split: the second slot and its code disappear at compile time).
+template <int N>
 struct Children {
   int n;
   double ox, oy, oz;    // lab origin
   double pl;            // _pathlength of the children
-  double dx[2], dy[2], dz[2], I[2], qre[2], qim[2], nmed[2];
+  double dx[N], dy[N], dz[N], I[N], qre[N], qim[N], nmed[N];
+  // slot k with k a run-time value: written as selects so that the arrays stay in registers
+  OPTB_DEV void set(int k, double ax, double ay, double az, double i, double qr, double qi, double nm) {
+#if OPTB_CH_REGS
+#pragma unroll
+    for (int j = 0; j < N; j++)
+      if (j == k) { dx[j] = ax; dy[j] = ay; dz[j] = az; I[j] = i; qre[j] = qr; qim[j] = qi; nmed[j] = nm; }
+#else
+    if (N == 1) k = 0;
+    dx[k] = ax; dy[k] = ay; dz[k] = az; I[k] = i; qre[k] = qr; qim[k] = qi; nmed[k] = nm;
+#endif
+  }
 };
 
 // local child direction -> lab (ray_to_lab_coordinates :119-124; both normalisations)
@@ -559,10 +642,10 @@ OPTB_DEV void dir_to_lab(const double* __restrict__ T, bool ortho, double lx, do
 }
 
 // interact_local bodies for the winning leaf. (ox..dz) is the ray in the leaf's local frame, t the hit parameter.
-template <bool ASPH>
+template <bool ASPH, int N>
 OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
                        const Ray& ray, double unit, double ox, double oy, double oz, double dx, double dy, double dz,
-                       double t, Children& ch, const IndexCache& ic) {
+                       double t, Children<N>& ch, const IndexCache& ic) {
   const double* T = nf + OPTB_NF_T;
   const double* c = nf + OPTB_NF_ORIGIN;
   const bool ortho = ni[OPTB_NI_ORTHO] != 0;
@@ -576,6 +659,7 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
   const double refl = nf[OPTB_NF_REFL], trans = nf[OPTB_NF_TRANS];
   ch.pl = fma(t, ray.n, ray.pl);  // Ray.pathlength ray.py:145-147
   if (kind == OPTB_I_ABSORB) return;  // Block :501-503
+  double gx, gy, gz;
   if (kind == OPTB_I_THINLENS) {      // Lens :930-948
     double f = nf[OPTB_NF_FOCAL];
     double qre = ray.qre, qim = ray.qim;
@@ -584,8 +668,8 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
       cdiv(q1r, q1i, 1.0 - q1r / f, -(q1i / f), qre, qim);
     }
     double inv_f = 1.0 / f;
-    dir_to_lab(T, ortho, dx - Px * inv_f, dy - Py * inv_f, dz - Pz * inv_f, ch.dx[0], ch.dy[0], ch.dz[0]);
-    ch.I[0] = ray.I * trans; ch.qre[0] = qre; ch.qim[0] = qim; ch.nmed[0] = ray.n;
+    dir_to_lab(T, ortho, dx - Px * inv_f, dy - Py * inv_f, dz - Pz * inv_f, gx, gy, gz);
+    ch.set(0, gx, gy, gz, ray.I * trans, qre, qim, ray.n);
     ch.pl = ray.pl;  // the thin lens leaves _pathlength untouched
     ch.n = 1;
     return;
@@ -597,12 +681,12 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
     double qre = ray.qre + t, qim = ray.qim;
     int k = 0;
     if (refl > 0) {
-      dir_to_lab(T, ortho, fma(-2 * dn, nx, dx), fma(-2 * dn, ny, dy), fma(-2 * dn, nz, dz), ch.dx[k], ch.dy[k], ch.dz[k]);
-      ch.I[k] = ray.I * refl; ch.qre[k] = qre; ch.qim[k] = qim; ch.nmed[k] = ray.n; k++;
+      dir_to_lab(T, ortho, fma(-2 * dn, nx, dx), fma(-2 * dn, ny, dy), fma(-2 * dn, nz, dz), gx, gy, gz);
+      ch.set(k, gx, gy, gz, ray.I * refl, qre, qim, ray.n); k++;
     }
-    if (trans > 0) {
-      dir_to_lab(T, ortho, dx, dy, dz, ch.dx[k], ch.dy[k], ch.dz[k]);
-      ch.I[k] = ray.I * trans; ch.qre[k] = qre; ch.qim[k] = qim; ch.nmed[k] = ray.n; k++;
+    if (trans > 0 && k < N) {
+      dir_to_lab(T, ortho, dx, dy, dz, gx, gy, gz);
+      ch.set(k, gx, gy, gz, ray.I * trans, qre, qim, ray.n); k++;
     }
     ch.n = k;
     return;
@@ -624,6 +708,7 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
   double sin_i = sqrt(1.0 - cos_i * cos_i);
   double sin_t = (nin * sin_i) / nout;
   const double ratio = nin / nout;  // D of the refraction ABCD and the tangential scale of Snell's law
+  const bool want_refl = (N > 1) && refl > 0;  // a scene whose interactions emit one ray at most has refl == 0 here
   double qtr = 0, qti = 0, qrr = 0, qri = 0;
   if (hasq) {  // ABCD of the refraction / of the reflection (:648-666); each only when a child will carry it
     double qr = ray.qre + t, qi = ray.qim;
@@ -631,7 +716,7 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
       double Cc = (nin - nout) / (ROC * nout);
       cdiv(qr, qi, fma(Cc, qr, ratio), Cc * qi, qtr, qti);
     }
-    if (!(sin_t < 1) || refl > 0) {
+    if (!(sin_t < 1) || want_refl) {
       double C2 = 2.0 / ROC;
       cdiv(qr, qi, fma(C2, qr, 1.0), C2 * qi, qrr, qri);
     }
@@ -639,24 +724,25 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
   // reflected direction d + 2 cos_i (-n)
   double rfx = fma(-2 * cos_i, nx, dx), rfy = fma(-2 * cos_i, ny, dy), rfz = fma(-2 * cos_i, nz, dz);
   int k = 0;
+  double g0x = 0, g0y = 0, g0z = 0;
   if (sin_t < 1) {
     if (trans > 0) {
       double cos_t = sqrt(1.0 - sin_t * sin_t);
       double kk = ratio, cs = cos_t * sgn;
-      dir_to_lab(T, ortho, fma(kk, rtx, cs * nx), fma(kk, rty, cs * ny), fma(kk, rtz, cs * nz), ch.dx[k], ch.dy[k], ch.dz[k]);
-      ch.I[k] = ray.I * trans; ch.qre[k] = qtr; ch.qim[k] = qti; ch.nmed[k] = nout; k++;
+      dir_to_lab(T, ortho, fma(kk, rtx, cs * nx), fma(kk, rty, cs * ny), fma(kk, rtz, cs * nz), g0x, g0y, g0z);
+      ch.set(0, g0x, g0y, g0z, ray.I * trans, qtr, qti, nout); k = 1;
     }
   } else {  // total internal reflection (also taken when sin_t is NaN, as `sin_t < 1` is False)
-    dir_to_lab(T, ortho, rfx, rfy, rfz, ch.dx[k], ch.dy[k], ch.dz[k]);
-    ch.I[k] = ray.I; ch.qre[k] = qrr; ch.qim[k] = qri; ch.nmed[k] = ray.n; k++;
+    dir_to_lab(T, ortho, rfx, rfy, rfz, g0x, g0y, g0z);
+    ch.set(0, g0x, g0y, g0z, ray.I, qrr, qri, ray.n); k = 1;
   }
-  if (refl > 0) {
+  if (want_refl) {
     if (k == 1 && !(sin_t < 1)) {  // TIR + reflectivity: same direction twice
-      ch.dx[1] = ch.dx[0]; ch.dy[1] = ch.dy[0]; ch.dz[1] = ch.dz[0];
+      gx = g0x; gy = g0y; gz = g0z;
     } else {
-      dir_to_lab(T, ortho, rfx, rfy, rfz, ch.dx[k], ch.dy[k], ch.dz[k]);
+      dir_to_lab(T, ortho, rfx, rfy, rfz, gx, gy, gz);
     }
-    ch.I[k] = ray.I * refl; ch.qre[k] = qrr; ch.qim[k] = qri; ch.nmed[k] = ray.n; k++;
+    ch.set(k, gx, gy, gz, ray.I * refl, qrr, qri, ray.n); k++;
   }
   ch.n = k;
 }

@@ -1,9 +1,11 @@
 """Run the REAL reference (tim4431/optable, Python) in the build container.
 
-TEST INFRASTRUCTURE ONLY. /root/reference does not exist on the GPU box, so nothing that runs there may
-call load_reference(); the results of this harness travel as fixtures (tests/golden/, made by
-oracle/make_golden.py). The reference is imported unmodified; matplotlib (not installed here, never
-called on the hot path) is replaced by empty stub modules.
+TEST INFRASTRUCTURE ONLY. /root/reference does not exist on the GPU box; what travels there is (a) the
+fixtures this harness produced (tests/golden/, made by oracle/make_golden.py) and (b) the UNMODIFIED reference
+package as `pip install --target baseline/_ref` put it (git-ignored, done by __graft_entry__.build()),
+which the `-m gpu` drop-in tests and the `kind: "reference"` leg of bench.py import from there. The reference is
+imported unmodified; matplotlib (not installed here, never called on the hot path) is replaced by empty stub
+modules.
 """
 from __future__ import annotations
 
@@ -14,12 +16,48 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("OPTABLE_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INSTALLED_ROOT = os.path.join(_REPO, "baseline", "_ref")  # pip --target copy of the reference (travels with gpurun)
+
+
+def _pick_root():
+    for cand in (os.environ.get("OPTABLE_REFERENCE_ROOT"), "/root/reference", INSTALLED_ROOT):
+        if cand and os.path.isdir(os.path.join(cand, "optable")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 _ref = None
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "optable"))
+
+
+def install_reference(force=False) -> str:
+    """`pip install --no-index --no-deps --target baseline/_ref` of the reference tree (from a /tmp copy: the
+    tree itself is read-only). Returns the target directory, or "" when /root/reference is absent (GPU box: the
+    copy made in the build container travelled with the snapshot)."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    if os.path.isdir(os.path.join(INSTALLED_ROOT, "optable")) and not force:
+        return INSTALLED_ROOT
+    src = "/root/reference"
+    if not os.path.isdir(os.path.join(src, "optable")):
+        return ""
+    tmp = tempfile.mkdtemp(prefix="optable_src_")
+    try:
+        work = os.path.join(tmp, "src")
+        shutil.copytree(src, work, ignore=shutil.ignore_patterns(".git", "docs"))
+        cmd = [sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation", "--no-deps", "--quiet",
+               "--find-links", "/opt/wheelhouse", "--upgrade", "--target", INSTALLED_ROOT, work]
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return INSTALLED_ROOT
 
 
 def load_reference():

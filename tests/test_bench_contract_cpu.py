@@ -16,7 +16,7 @@ def _run(*args, env=None):
 
 
 def test_reference_arm_line():
-    run = _run("--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-rays", "3000")
+    run = _run("--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-rays", "3000", "--pyref-rays", "16")
     assert run.returncode == 0, run.stderr[-2000:]
     lines = [l for l in run.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -28,10 +28,17 @@ def test_reference_arm_line():
     assert d["value"] > 1e4 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["vs_baseline"] is None
     assert d["config"]["workload"] == "c2_4f_telescope"
+    # beside the C port: the unmodified Python reference (pip --target copy or /root/reference), one process per core
+    py = d["cpu_baseline_reference"]
+    from oracle import ref_harness as RH
+
+    if RH.reference_available():
+        assert py["kind"] == "reference" and py["value"] > 1 and py["cores"] >= 1
+        assert d["value"] > 20 * py["value"]  # the port arm is the conservative (much faster) CPU denominator
 
 
 def test_reference_arm_other_ranks_do_nothing():
-    run = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-rays", "1000", env={"RANK": "1", "WORLD_SIZE": "2"})
+    run = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-rays", "1000", "--pyref-rays", "8", env={"RANK": "1", "WORLD_SIZE": "2"})
     assert run.returncode == 0 and run.stdout.strip() == ""
 
 

@@ -176,3 +176,22 @@ def test_pipelined_host_trace_equals_device_trace(engine):
     assert torch.equal(ka, kb)
     for k in dt.hit_columns:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_one_ray_whose_generation_outgrows_64_live_rays(engine):
+    """the wavefront capacity used to be clamped to 64x the batch, so ONE initial ray through a stack of
+    partial mirrors (every pop queues two rays) overflowed the workspace although the reference traces it to its
+    2000-pop cap. The capacity now follows the workspace and `trace_arrays` grows it on overflow."""
+    import optable_b200 as ob
+
+    comps = [ob.Mirror([float(x), 0, 0], radius=3, reflectivity=0.6, transmission=0.4).RotZ(0.002 * k)
+             for k, x in enumerate(range(0, 16, 2))]
+    sc = scenes.Scene(comps, [], [ob.Monitor([20, 0, 0], 8, 8)])
+    arrs = scenes.ray_arrays(1, [-1, 0.01, 0.02], [0, 0, 0], [1, 0, 0], [0, 0, 0])
+    got, errs = _both(engine, sc, arrs, limit=2000, nthreads=1)
+    assert len(got["seg_root"]) == 2000 and int(got["counters"][4]) > 64  # the pop cap bound with > 64 rays still queued
+    # same through the object API (trace_table has no max_live knob: it must grow on its own)
+    table = ob.OpticalTable()
+    table.add_components(comps)
+    ray = ob.Ray([-1, 0.01, 0.02], [1, 0, 0], wavelength=780e-7, w0=61e-4)
+    assert len(table.ray_tracing(ray)) == 2000

@@ -37,56 +37,15 @@ class OracleEngine:
         return out
 
 
-def _fields(r):
-    return (np.array(r.origin, float), np.array(r.direction, float), r.length, bool(r.alive), float(r.intensity),
-            float(r.wavelength), r.qo, float(r._pathlength), float(r.n), r._id)
+from tests.install_check import fields as _fields  # noqa: E402
 
 
 @pytest.mark.parametrize("name", ["gaussian_beam", "chromatic", "doublet", "telescope_4f", "prism_refl", "caps_binding",
                                   "dove_prism", "misc_components", "mma_small"])
 def test_installed_backend_equals_original_method(name):
-    import optable_b200
+    from tests.install_check import check_install
 
-    ref = RH.load_reference()
-    a, b = scenes.REGISTRY[name](ref), scenes.REGISTRY[name](ref)
-    ta, tb = ref.OpticalTable(), ref.OpticalTable()
-    for t, sc in ((ta, a), (tb, b)):
-        t.add_components(sc.components)
-        t.add_monitors(sc.monitors)
-    want = ta.ray_tracing(a.rays, perfomance_limit=a.limit)          # the reference's own method
-    original = optable_b200.install(ref, engine=OracleEngine())
-    try:
-        got = tb.ray_tracing(b.rays, perfomance_limit=b.limit)       # same call, swapped back end
-    finally:
-        ref.OpticalTable.ray_tracing = original
-    assert len(got) == len(want) == len(tb.rays)
-    for rw, rg in zip(ta.rays, tb.rays):
-        fw, fg = _fields(rw), _fields(rg)
-        assert parity._rel_vec(fw[0], fg[0], 1.0) <= 1e-9 and parity._rel_vec(fw[1], fg[1], 1.0) <= 1e-9
-        assert (fw[2] is None) == (fg[2] is None) and (fw[2] is None or abs(fw[2] - fg[2]) <= 1e-9 * max(abs(fw[2]), 1e-3))
-        assert fw[3] == fg[3] and fw[4] == pytest.approx(fg[4], rel=1e-9) and fw[5] == fg[5]
-        assert (fw[6] is None) == (fg[6] is None) and (fw[6] is None or abs(fw[6] - fg[6]) <= 1e-9 * abs(fw[6]))
-        assert fw[7] == pytest.approx(fg[7], rel=1e-9, abs=1e-12) and fw[8] == pytest.approx(fg[8], rel=1e-12)
-    # ids: the reference keys families by Ray._id; copies made by the two scene builds differ in id(), so compare
-    # the partition of segments into families instead of the raw values
-    fam_w = {}
-    fam_g = {}
-    for k, (rw, rg) in enumerate(zip(ta.rays, tb.rays)):
-        fam_w.setdefault(rw._id, []).append(k)
-        fam_g.setdefault(rg._id, []).append(k)
-    assert sorted(fam_w.values()) == sorted(fam_g.values())
-    for mw, mg in zip(ta.monitors, tb.monitors):
-        assert len(mw._data_raw) == len(mg._data_raw) and mg._updated
-        for (Pw, Iw, tw, rw), (Pg, Ig, tg, rg) in zip(mw._data_raw, mg._data_raw):
-            assert np.linalg.norm(np.asarray(Pw) - np.asarray(Pg)) <= 1e-9 * max(np.linalg.norm(Pw), 1.0)
-            assert Iw == pytest.approx(Ig, rel=1e-9) and tw == pytest.approx(tg, rel=1e-9)
-            assert any(rg is s for s in tb.rays)      # rows reference the segment objects of table.rays
-        if mw._data_raw:                              # the reference's accessors run on backend-filled monitors
-            np.testing.assert_allclose(mg.get_yList(), mw.get_yList(), rtol=1e-9, atol=1e-12)  # YZ order: ids are id() values
-            np.testing.assert_allclose(mg.get_tYList(), mw.get_tYList(), rtol=1e-9, atol=1e-12)
-    leaves_w, leaves_g = RH._leaves(ta.components, []), RH._leaves(tb.components, [])
-    for cw, cg in zip(leaves_w, leaves_g):
-        assert sorted(cw._interact_count.values()) == sorted(cg._interact_count.values()) or cw.max_interact_count is None
+    check_install(name, OracleEngine())
 
 
 @pytest.mark.parametrize("name", ["gaussian_beam", "chromatic", "telescope_4f", "prism_refl", "misc_components"])
