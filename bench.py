@@ -348,6 +348,7 @@ def measure(args, D, engine, name, steps, warmup, e2e_steps, with_cpu, peaks, fp
     del rays_dev
     engine._workspace = None
     torch.cuda.empty_cache()
+    flushed = flush is not None
     del flush
     e2e, e2e_hist = run_e2e(args, D, engine, dt, bundle, n, hit_cap, hit_columns, hit_dtypes, row_bytes, hist_shapes, inter,
                             hits, inter_all, e2e_steps)
@@ -359,7 +360,7 @@ def measure(args, D, engine, name, steps, warmup, e2e_steps, with_cpu, peaks, fp
                       "leaf_tests_per_step_per_gpu": tests, "curved_leaf_tests_per_step_per_gpu": curved,
                       "box_tests_per_step_per_gpu": boxes,
                       "monitor_row_bytes": row_bytes,
-                      "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2" % (step_bytes / 1e9) if flush is None else
+                      "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2" % (step_bytes / 1e9) if not flushed else
                             "inputs+outputs per step (%.3f GB) fit the L2: a 256 MB buffer is written between timed steps (inside ms_per_step)" % (step_bytes / 1e9),
                       "parallelism": f"rays sharded over {D.world} GPU(s), scene tables replicated, histograms all-reduced"},
            "clocks": clocks, "gpu_launches": launches * steps, "e2e": e2e}
@@ -406,6 +407,7 @@ def rooflines(name, n, inter, pops, hits, tests, curved, boxes, row_bytes, bundl
              "convention": "persistent form: 208 B per initial ray (record read + written once) + monitor row bytes; "
                            "SURVEY 8(d)'s wavefront-form figure (208 B per interaction) would be %.1f GB/s" % (208 * inter / sec / 1e9)}
     r_fp = {"bound": "fp64", "achieved": a_fp, "peak": fp64_peak["tflops"], "unit": "TFLOP/s", "frac": a_fp / fp64_peak["tflops"],
+            "traffic": None,
             "peak_source": "measured in this run: optb_measure_fp64_peak (8 independent DFMA chains per thread), SM clock %s MHz while it ran" % fp64_peak.get("sm_mhz"),
             "kernel": "trace_kernel", "kernel_ms": trace_ms, "algorithmic_flops": int(flops),
             "flops_per_interaction": flops / max(inter, 1),

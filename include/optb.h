@@ -53,6 +53,10 @@ enum {
   OPTB_G_CYL = 5,     /* Cylinder      surfaces.py:212-281   p0 = r, p1 = height, p2 = theta0, p3 = theta1 */
   OPTB_G_POLY2D = 6,  /* Polygon, planar=True   surfaces.py:426-568   aux -> polygon record */
   OPTB_G_POLY3D = 7,  /* Polygon, planar=False  (curved branch, linear f)  aux -> polygon record */
+  OPTB_G_GRID = 9,    /* a ComponentGroup whose leaf children sit on a regular 2-D lattice (MMA, MLA, DMD:
+                         component_group.py:228-391): a group for every purpose, plus a lattice descriptor in the aux
+                         pool (NI_AUX) from which the device lists the few cells a ray can reach instead of
+                         descending a box hierarchy over thousands of children. See OPTB_GRID_* below.         */
   OPTB_G_CSG = 8      /* Plane.union / Plane.subtract  surfaces.py:100-136
                          p0 = op (0 = A and not B, 1 = A or B),
                          p1 = kind A, p2,p3 = params A (or aux offset for poly),
@@ -115,6 +119,19 @@ enum {
  * [0] nverts, [1..3] unit normal, [4..6] vertices[0], [7..9] basis u, [10..12] basis v,
  * [13..18] bbox, [19 ..] verts2d as (x,y) pairs.                                    */
 enum { OPTB_POLY_HEADER = 19 };
+
+/* lattice descriptor of an OPTB_G_GRID node in the aux pool (doubles). Child k = i * n_inner + j of the group (list
+ * order, component_group.py:104-115) has the centre of its lab box within `R - |half diagonal|` of
+ * c00 + i U + j V. A ray can only pass the reference's own box test of child (i, j) at a point P with
+ * |P - (c00 + i U + j V)| <= R, i.e. |(P - c00).nhat| <= R, |(P - c00).Ud - i| <= rho_a, |(P - c00).Vd - j| <= rho_b
+ * (Ud, Vd: dual basis of U, V in the lattice plane). The device tests exactly the children inside that window with
+ * their own stored boxes: a superset of what the reference's test passes, so the tested set is the reference's.   */
+enum {
+  OPTB_GRID_NOUTER = 0, OPTB_GRID_NINNER = 1, OPTB_GRID_NEXT = 2, /* lattice size; children outside the lattice (tested always) */
+  OPTB_GRID_R = 3, OPTB_GRID_C00 = 4, OPTB_GRID_NHAT = 7, OPTB_GRID_UD = 10, OPTB_GRID_VD = 13,
+  OPTB_GRID_RHOA = 16, OPTB_GRID_RHOB = 17,
+  OPTB_GRID_CELLS = 18 /* node index of every lattice child (n_outer * n_inner doubles), then of the extra children */
+};
 
 /* material table (optable/material.py): kind 0 = constant n (f[0]),
  * kind 1 = Sellmeier-3 (f[0..2] = B, f[3..5] = C in um^2)                  :93-120,

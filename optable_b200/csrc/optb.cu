@@ -29,8 +29,8 @@ namespace {
 #ifndef OPTB_MIN_BLOCKS
 #define OPTB_MIN_BLOCKS 4
 #endif
-#ifndef OPTB_LAZY_BOXES
-#define OPTB_LAZY_BOXES 0   // measured on B200 (r2a): the lab boxes cull 30-35 % of the leaf tests of lens groups; testing every leaf first costs more (c3 8.2 -> 9.0 ms)
+#ifndef OPTB_GRID_WALK
+#define OPTB_GRID_WALK 1   // 0: ignore the lattice descriptors (A/B switch; OPTB_G_GRID nodes are then plain groups)
 #endif
 constexpr int kBlock = 128;
 constexpr int kTile = 2048;  // children-scan tile (entries per block)
@@ -289,13 +289,43 @@ struct HitSearch {
   }
 };
 
+// Lattice window of a ray in an OPTB_G_GRID group (descriptor layout: include/optb.h OPTB_GRID_*): index ranges
+// [i0, i1] x [j0, j1] of the children whose lab box the ray can touch. False = no cheap window (ray nearly in the
+// lattice plane, or more than 64 cells): the caller descends the group's box hierarchy instead.
+OPTB_DEV bool grid_window(const double* __restrict__ gd, const Ray& r, int& i0, int& i1, int& j0, int& j1) {
+  const double R = gd[OPTB_GRID_R];
+  const double px = r.ox - gd[OPTB_GRID_C00], py = r.oy - gd[OPTB_GRID_C00 + 1], pz = r.oz - gd[OPTB_GRID_C00 + 2];
+  const double w0 = dot3(px, py, pz, gd[OPTB_GRID_NHAT], gd[OPTB_GRID_NHAT + 1], gd[OPTB_GRID_NHAT + 2]);
+  const double wd = dot3(r.dx, r.dy, r.dz, gd[OPTB_GRID_NHAT], gd[OPTB_GRID_NHAT + 1], gd[OPTB_GRID_NHAT + 2]);
+  if (!(fabs(wd) >= 1e-3)) return false;
+  // |w0 + t wd| <= R, t >= 0
+  const double inv = 1.0 / wd;
+  double ta = (-R - w0) * inv, tb = (R - w0) * inv;
+  if (ta > tb) { const double x = ta; ta = tb; tb = x; }
+  i0 = j0 = 0; i1 = j1 = -1;
+  if (!(tb >= 0.0)) return true;  // the lattice slab lies behind the ray: no lattice child can pass its box test
+  ta = fmax(ta, 0.0);
+  const double a0 = dot3(px, py, pz, gd[OPTB_GRID_UD], gd[OPTB_GRID_UD + 1], gd[OPTB_GRID_UD + 2]);
+  const double ad = dot3(r.dx, r.dy, r.dz, gd[OPTB_GRID_UD], gd[OPTB_GRID_UD + 1], gd[OPTB_GRID_UD + 2]);
+  const double b0 = dot3(px, py, pz, gd[OPTB_GRID_VD], gd[OPTB_GRID_VD + 1], gd[OPTB_GRID_VD + 2]);
+  const double bd = dot3(r.dx, r.dy, r.dz, gd[OPTB_GRID_VD], gd[OPTB_GRID_VD + 1], gd[OPTB_GRID_VD + 2]);
+  const double a1 = fma(ta, ad, a0), a2 = fma(tb, ad, a0), b1 = fma(ta, bd, b0), b2 = fma(tb, bd, b0);
+  const double no = gd[OPTB_GRID_NOUTER] - 1.0, ni = gd[OPTB_GRID_NINNER] - 1.0;
+  const double alo = ceil(fmin(a1, a2) - gd[OPTB_GRID_RHOA]), ahi = floor(fmax(a1, a2) + gd[OPTB_GRID_RHOA]);
+  const double blo = ceil(fmin(b1, b2) - gd[OPTB_GRID_RHOB]), bhi = floor(fmax(b1, b2) + gd[OPTB_GRID_RHOB]);
+  if (!(alo <= ahi && blo <= bhi)) return alo == alo && ahi == ahi && blo == blo && bhi == bhi;  // empty (NaN: no window)
+  if (ahi < 0.0 || alo > no || bhi < 0.0 || blo > ni) return true;  // window beside the lattice
+  i0 = (int)fmax(alo, 0.0); i1 = (int)fmin(ahi, no);
+  j0 = (int)fmax(blo, 0.0); j1 = (int)fmin(bhi, ni);
+  if ((i1 - i0 + 1) * (j1 - j0 + 1) > 64) { i1 = j1 = -1; return false; }
+  return true;
+}
+
 // BOXES: 0 = the scene has no lab-box test at all (top-level leaves only);
 //        1 = pre-order walk, a failed box test skips the subtree (component_group.py:98-115 as a forward scan);
-//        2 = small scenes (<= 32 nodes, no interact caps): every leaf is tested first and only the WINNER's boxes
-//            (its own and its ancestors') are checked afterwards. A leaf the reference would have culled can only
-//            change the result by winning, and a winner whose box chain fails is struck out together with the
-//            failed subtree and the search repeated: the outcome is the reference's, at two box tests per pop
-//            instead of one per node (a lens group of 2-3 faces: 4-8 per pop).
+//        2 = the same walk, and groups whose children form a regular lattice (OPTB_G_GRID: MMA / MLA / DMD arrays)
+//            hand the walk the few children inside the ray's lattice window instead of a descent through their
+//            box hierarchy; each candidate still has to pass the reference's own test of its own box.
 template <int BOXES, bool ASPH>
 OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
                           double& best_t, int& best_node, unsigned int* cnt) {
@@ -309,9 +339,10 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   int i = 0;
   const int n = sv.n_nodes;
   // BOXES = 0: a scene of top-level leaves only has no box test at all (and pays no reciprocals for one)
-  // (BOXES = 2 builds it when the winner is verified: 18 registers less during the leaf tests)
-  const BoxRay br(ray.ox, ray.oy, ray.oz, BOXES == 1 ? ray.dx : 1.0, BOXES == 1 ? ray.dy : 1.0, BOXES == 1 ? ray.dz : 1.0);
-  unsigned excl = 0u;  // BOXES == 2: nodes whose subtree the ray is known to miss by a box test
+  const BoxRay br(ray.ox, ray.oy, ray.oz, BOXES ? ray.dx : 1.0, BOXES ? ray.dy : 1.0, BOXES ? ray.dz : 1.0);
+  // lattice cursor (BOXES = 2): group being listed (-1: none), cell cursor, window, cursor over the extra children
+  int g_node = -1, g_i = 0, g_j = 0, g_i1 = -1, g_j0 = 0, g_j1 = -1, g_x = 0;
+  const double* gd = nullptr;
   // Warp-synchronous "walk, then test": in every round each lane walks boxes until it holds a leaf (or runs out of
   // nodes and takes a parked asphere), then the lanes that called in together meet again at the vote and run the
   // one, long leaf test side by side. Without the explicit vote the compiler is free to fold the test into the
@@ -319,21 +350,46 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   // (measured: 3x on the 7,689-leaf scene). One test_leaf call site also keeps the kernel's code size down.
   const unsigned group = __activemask();
   bool searching = !no_work;
-  // (scenes without box walk yield a leaf per walk step: all lanes are in lock-step anyway, no vote needed)
-  while (BOXES == 1 ? __any_sync(group, searching) : searching) {
+  // (scenes without box tests yield a leaf per walk step: all lanes are in lock-step anyway, no vote needed)
+  while (BOXES ? __any_sync(group, searching) : searching) {
     int leaf = -1;
     if (searching) {
-      while (i < n) {
+      while (true) {
+        if (BOXES == 2 && g_node >= 0) {
+          // next candidate child of the lattice group: window cells in list order, then the off-lattice children
+          int cand;
+          if (g_i <= g_i1) {
+            cand = (int)gd[OPTB_GRID_CELLS + g_i * (int)gd[OPTB_GRID_NINNER] + g_j];
+            if (++g_j > g_j1) { g_j = g_j0; g_i++; }
+          } else if (g_x < (int)gd[OPTB_GRID_NEXT]) {
+            cand = (int)gd[OPTB_GRID_CELLS + (int)gd[OPTB_GRID_NOUTER] * (int)gd[OPTB_GRID_NINNER] + g_x];
+            g_x++;
+          } else {  // done: leave the group's subtree
+            i = reinterpret_cast<const int2*>(sv.trav + g_node * 8 + 6)->y;
+            g_node = -1;
+            continue;
+          }
+          n_box++;
+          if (!slab_hit(br, sv.trav + cand * 8)) continue;  // the child's own lab box (component_group.py:104-107)
+          leaf = cand;  // (lattice children are leaves without interact caps, never aspheres to park: flatten._grid)
+          break;
+        }
+        if (i >= n) break;
         const double* tv = sv.trav + i * 8;
         const int2 gs = *reinterpret_cast<const int2*>(tv + 6);  // {geometry kind, skip}
-        if (BOXES == 1 && *reinterpret_cast<const int*>(tv + 7)) {
+        if (BOXES && *reinterpret_cast<const int*>(tv + 7)) {
           n_box++;
           if (!slab_hit(br, tv)) { i = gs.y; continue; }
         }
-        if (BOXES == 2 && ((excl >> i) & 1u)) { i = gs.y; continue; }
         const int g = gs.x;
         const int cur = i++;
-        if (g == OPTB_G_GROUP) continue;
+        if (BOXES == 2 && g == OPTB_G_GRID && !br.any_par) {
+          gd = sv.aux + sv.ni[cur * OPTB_NI_STRIDE + OPTB_NI_AUX];
+          int i0;
+          if (grid_window(gd, ray, i0, g_i1, g_j0, g_j1)) { g_node = cur; g_i = i0; g_j = g_j0; g_x = 0; }
+          continue;  // (no window: fall through into the box hierarchy below this node)
+        }
+        if (g == OPTB_G_GROUP || g == OPTB_G_GRID) continue;
         if (ASPH && g == OPTB_G_ASPHERE && n_parked < kPark) {
 #pragma unroll
           for (int k = 0; k < kPark; k++) if (k == n_parked) parked[k] = cur;
@@ -348,24 +404,6 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
 #pragma unroll
           for (int k = 0; k < kPark; k++) if (k == n_done) leaf = parked[k];
           n_done++;
-        } else if (BOXES == 2 && hs.best_node >= 0) {
-          // every leaf tested: the winner must also pass its own box and those of its ancestors
-          int bad = -1;
-          const BoxRay vr(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz);
-          for (int j = hs.best_node; j >= 0;) {
-            const double* tv = sv.trav + j * 8;
-            const int2 fp = *reinterpret_cast<const int2*>(tv + 7);  // {box-test flag, parent}
-            if (fp.x) { n_box++; if (!slab_hit(vr, tv)) bad = j; }  // keeps the outermost failing node
-            j = fp.y;
-          }
-          if (bad < 0) {
-            searching = false;
-          } else {  // strike the failed subtree out and search again (rare: stale or under-covering boxes)
-            const int end = reinterpret_cast<const int2*>(sv.trav + bad * 8 + 6)->y;
-            excl |= (end >= 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << bad) - 1u);
-            hs.best_t = INFINITY; hs.best_node = -1;
-            i = 0; n_parked = 0; n_done = 0;
-          }
         } else {
           searching = false;
         }
@@ -757,7 +795,7 @@ struct optb_ctx {
 struct optb_scene {
   unsigned char* d_blob; size_t blob_cap; uint32_t blob_bytes; SceneOff off;
   int n_nodes, n_leaves, n_mats, n_mons, n_caps; long long n_aux;
-  int max_children; int has_boxes; int has_asph; int lazy_boxes;
+  int max_children; int has_boxes; int has_asph; int has_grid;
   bool in_smem; bool hist_smem; uint32_t smem_bytes;
   // recorded on the stream of every trace that reads the blob: releasing the scene waits for this event only,
   // not for the whole device (other streams, NCCL and unrelated kernels keep running)
@@ -824,8 +862,23 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
     const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
     const int g = ni[OPTB_NI_GEOM];
     if (ni[OPTB_NI_SKIP] <= i || ni[OPTB_NI_SKIP] > d->n_nodes) return fail(ctx, -5, "scene: node skip pointer out of range");
-    if (g < OPTB_G_GROUP || g > OPTB_G_CSG) return fail(ctx, -5, "scene: unknown geometry kind");
-    if (g == OPTB_G_GROUP) continue;
+    if (g < OPTB_G_GROUP || g > OPTB_G_GRID) return fail(ctx, -5, "scene: unknown geometry kind");
+    if (g == OPTB_G_GRID) {  // lattice descriptor: inside the aux pool, every listed child a leaf of this subtree
+      const long long off = ni[OPTB_NI_AUX];
+      if (off < 0 || off + OPTB_GRID_CELLS > d->n_aux) return fail(ctx, -5, "scene: lattice descriptor out of range");
+      const double* gd = d->aux + off;
+      const double cells = gd[OPTB_GRID_NOUTER] * gd[OPTB_GRID_NINNER] + gd[OPTB_GRID_NEXT];
+      if (!(gd[OPTB_GRID_NOUTER] >= 1 && gd[OPTB_GRID_NINNER] >= 1 && gd[OPTB_GRID_NEXT] >= 0 && cells <= 1e8) ||
+          off + OPTB_GRID_CELLS + (long long)cells > d->n_aux)
+        return fail(ctx, -5, "scene: lattice descriptor out of range");
+      for (long long k = 0; k < (long long)cells; k++) {
+        const double c = gd[OPTB_GRID_CELLS + k];
+        if (!(c > i && c < ni[OPTB_NI_SKIP]) || d->node_i[(size_t)c * OPTB_NI_STRIDE + OPTB_NI_GEOM] == OPTB_G_GROUP ||
+            d->node_i[(size_t)c * OPTB_NI_STRIDE + OPTB_NI_GEOM] == OPTB_G_GRID)
+          return fail(ctx, -5, "scene: lattice child is not a leaf of the group's subtree");
+      }
+    }
+    if (g == OPTB_G_GROUP || g == OPTB_G_GRID) continue;
     if (ni[OPTB_NI_SKIP] != i + 1) return fail(ctx, -5, "scene: a leaf must skip to the next node");
     if (ni[OPTB_NI_INTER] < OPTB_I_MIRROR || ni[OPTB_NI_INTER] > OPTB_I_ABSORB) return fail(ctx, -5, "scene: unknown interaction kind");
     if (ni[OPTB_NI_MAT1] < 0 || ni[OPTB_NI_MAT1] >= d->n_materials || ni[OPTB_NI_MAT2] < 0 || ni[OPTB_NI_MAT2] >= d->n_materials)
@@ -879,7 +932,7 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
       const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
       while (!open.empty() && d->node_i[(size_t)open.back() * OPTB_NI_STRIDE + OPTB_NI_SKIP] <= i) open.pop_back();
       parent[i] = open.empty() ? -1 : open.back();
-      if (ni[OPTB_NI_GEOM] == OPTB_G_GROUP) open.push_back(i);
+      if (ni[OPTB_NI_GEOM] == OPTB_G_GROUP || ni[OPTB_NI_GEOM] == OPTB_G_GRID) open.push_back(i);
     }
     for (int i = 0; i < d->n_nodes; i++) {  // compact traversal records
       unsigned char* tv = host.data() + s->off.trav + (size_t)i * 64;
@@ -900,6 +953,7 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
     const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
     if (ni[OPTB_NI_AABB]) s->has_boxes = 1;
     if (ni[OPTB_NI_GEOM] == OPTB_G_ASPHERE) s->has_asph = 1;
+    if (ni[OPTB_NI_GEOM] == OPTB_G_GRID) s->has_grid = 1;
     int k = 0;
     switch (ni[OPTB_NI_INTER]) {
       case OPTB_I_MIRROR: k = (nf[OPTB_NF_REFL] > 0) + (nf[OPTB_NF_TRANS] > 0); break;
@@ -916,10 +970,6 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   size_t used = s->in_smem ? o : 0;
   s->hist_smem = (hist_bytes > 0 && used + hist_bytes <= std::min<size_t>(budget, used + 65536));
   s->smem_bytes = (uint32_t)(used + (s->hist_smem ? hist_bytes : 0));
-  // winner-verified box tests (closest_hit BOXES = 2): the struck-out set is one 32-bit mask, interact caps count
-  // every geometric hit of a leaf whose boxes pass (so they need the culling walk), and only shared-memory scenes
-  // test leaves cheaply enough for "test all, verify one" to win
-  s->lazy_boxes = (OPTB_LAZY_BOXES && s->in_smem && s->has_boxes && d->n_capslots == 0 && d->n_nodes <= 32) ? 1 : 0;
   cudaError_t e = cudaSuccess;
   int pick = -1;  // smallest retired blob that is large enough
   for (int k = 0; k < 8; k++)
@@ -1130,13 +1180,13 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   }
   uint32_t smem = scene->in_smem ? scene->smem_bytes : (a.hist_smem ? scene->smem_bytes : 0);
   using Kern = void (*)(const TraceArgs);
-  // box mode: 0 none, 1 pre-order walk with culling, 2 winner-verified (small shared-memory scenes without caps)
-  const int boxmode = !scene->has_boxes ? 0 : (scene->lazy_boxes ? 2 : 1);
-  // [smem][box mode][aspheres][split] for the parallel path (box mode 2 only exists with the tables in shared
-  // memory); the family-serial path keeps one general variant per staging mode
+  // box mode: 0 none, 1 pre-order walk with culling, 2 walk + lattice windows (scenes with OPTB_G_GRID groups)
+  const int boxmode = !scene->has_boxes ? 0 : ((scene->has_grid && OPTB_GRID_WALK) ? 2 : 1);
+  // [smem][box mode][aspheres][split] for the parallel path; the family-serial path keeps one general variant per
+  // staging mode
 #define OPTB_K(S, B, A, P) trace_kernel<S, false, B, A, P>
 #define OPTB_KROW(S, B) {{OPTB_K(S, B, false, false), OPTB_K(S, B, false, true)}, {OPTB_K(S, B, true, false), OPTB_K(S, B, true, true)}}
-  static const Kern table[2][3][2][2] = {{OPTB_KROW(false, 0), OPTB_KROW(false, 1), OPTB_KROW(false, 1)},
+  static const Kern table[2][3][2][2] = {{OPTB_KROW(false, 0), OPTB_KROW(false, 1), OPTB_KROW(false, 2)},
                                          {OPTB_KROW(true, 0), OPTB_KROW(true, 1), OPTB_KROW(true, 2)}};
 #undef OPTB_KROW
 #undef OPTB_K

@@ -12,7 +12,8 @@
 
 #define OPTB_DEV __device__ __forceinline__
 #ifndef OPTB_CH_REGS
-#define OPTB_CH_REGS 1   // Children slots written through selects (registers) instead of indexed stores (local memory)
+#define OPTB_CH_REGS 0   // 1: Children slots written through selects (registers) instead of indexed stores (local
+                         // memory). Measured on B200 (r2a): no difference on c2/c3/c4; 0 has fewer spills
 #endif
 #ifndef OPTB_STAGED_PLANAR
 #define OPTB_STAGED_PLANAR 1  // planar leaves: x row of Tinv first (intersect_planar) instead of a full to_local

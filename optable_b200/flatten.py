@@ -126,10 +126,14 @@ class FlatScene:
         self.capslots = []     # cap slot -> component object
         self.max_children = 0  # most rays one interaction can emit (<=1: no splitting anywhere)
         self._pending_inv = []
+        self._grids = []       # (aux offset of the cell table, [child node_i rows in list order]) per lattice group
         for c in components:
             tree = self._visit(c, in_group=False)
             if tree is not None:
                 self._emit(tree)
+        for off, rows in self._grids:  # node indices are only known after emission
+            self._aux[off:off + len(rows)] = [float(r[A.NI_SKIP] - 1) for r in rows]  # a leaf skips to index + 1
+        del self._grids
         if self._pending_inv:
             # np.linalg.inv on the stack runs the same per-matrix LAPACK solve as the reference's call per
             # component (optical_component.py:108): identical bits, ~30x less Python overhead
@@ -170,6 +174,73 @@ class FlatScene:
     # order, are exactly the reference's (component_group.py:104-115), only reached in O(log n) box tests.
     BVH_FANOUT = int(os.environ.get("OPTB_BVH_FANOUT", "4"))
     BVH_MIN_CHILDREN = int(os.environ.get("OPTB_BVH_MIN_CHILDREN", "9"))
+
+    GRID_MIN_CHILDREN = int(os.environ.get("OPTB_GRID_MIN_CHILDREN", "32"))
+
+    def _grid(self, ni, children):
+        """Regular arrays (MMA / MLA / DMD, component_group.py:228-391): when the lab boxes of a group's leaf children
+        sit on a 2-D lattice c00 + i U + j V (list order k = i * n_inner + j; up to 8 trailing children may be off the
+        lattice, e.g. the back face of an MMA), write the lattice descriptor of include/optb.h (OPTB_GRID_*) into the
+        aux pool and mark the group OPTB_G_GRID. Pure geometry of the children's own boxes: nothing here depends on
+        the class of the group. The box hierarchy over the children is still emitted; it serves rays for which the
+        lattice window would be large (in-plane rays) or the slab test takes its parallel-axis branch."""
+        if any(c[0][A.NI_GEOM] in (A.G_GROUP, A.G_GRID) or c[0][A.NI_CAPSLOT] >= 0 for c in children):
+            return
+        B = np.array([c[1][A.NF_AABB:A.NF_AABB + 6] for c in children], dtype=np.float64)
+        C, H = (B[:, 0::2] + B[:, 1::2]) / 2, (B[:, 1::2] - B[:, 0::2]) / 2
+        n = len(children)
+        V = C[1] - C[0]
+        pitch = float(np.linalg.norm(V))
+        if not pitch > 0:
+            return
+        tol = 0.02 * pitch
+        step = np.linalg.norm(np.diff(C, axis=0) - V, axis=1)          # deviation of every first difference from V
+        breaks = np.nonzero(step > tol)[0]
+        n_inner = int(breaks[0]) + 1 if len(breaks) else n
+        n_outer = 1
+        if n_inner < n:
+            U = C[n_inner] - C[0]
+            n_outer = 1
+            while (n_outer + 1) * n_inner <= n:
+                k0 = n_outer * n_inner
+                pred = C[0] + n_outer * U + np.arange(n_inner)[:, None] * V
+                if np.linalg.norm(C[k0:k0 + n_inner] - pred, axis=1).max() > 4 * tol:
+                    break
+                n_outer += 1
+        m = n_outer * n_inner
+        if n - m > 8 or m < self.GRID_MIN_CHILDREN:
+            return
+        if n_inner > 1:
+            V = (C[n_inner - 1] - C[0]) / (n_inner - 1)
+        if n_outer > 1:
+            U = (C[(n_outer - 1) * n_inner] - C[0]) / (n_outer - 1)
+        else:  # one row: complete the plane with the direction in which the boxes are thinnest
+            e = np.identity(3)[int(np.argmin(H[:m].max(axis=0)))]
+            nh = e - (e @ V) * V / (V @ V)
+            if np.linalg.norm(nh) < 1e-6:
+                return
+            nh /= np.linalg.norm(nh)
+            U = np.cross(nh, V)
+        nhat = np.cross(U, V)
+        if np.linalg.norm(nhat) < 1e-12 * np.linalg.norm(U) * np.linalg.norm(V):
+            return
+        nhat /= np.linalg.norm(nhat)
+        ii, jj = np.divmod(np.arange(m), n_inner)
+        L = C[0] + ii[:, None] * U + jj[:, None] * V
+        dev = np.linalg.norm(C[:m] - L, axis=1)
+        R = float((np.linalg.norm(H[:m], axis=1) + dev).max()) * (1 + 1e-6) + 1e-9 * (1.0 + float(np.abs(C).max()))
+        Ud = np.cross(V, nhat) / (U @ np.cross(V, nhat))
+        Vd = np.cross(nhat, U) / (V @ np.cross(nhat, U))
+        rho_a, rho_b = R * float(np.linalg.norm(Ud)), R * float(np.linalg.norm(Vd))
+        if rho_a > 2.0 or rho_b > 2.0:
+            return  # boxes much larger than the lattice spacing: the window would hold too many cells to pay off
+        off = len(self._aux)
+        self._aux.extend([float(n_outer), float(n_inner), float(n - m), R, *C[0].tolist(), *nhat.tolist(), *Ud.tolist(),
+                          *Vd.tolist(), rho_a, rho_b])
+        assert len(self._aux) - off == A.GRID_CELLS
+        self._grids.append((len(self._aux), [c[0] for c in children]))
+        self._aux.extend([0.0] * n)
+        ni[A.NI_GEOM], ni[A.NI_AUX] = A.G_GRID, off
 
     @staticmethod
     def _blank():
@@ -275,6 +346,8 @@ class FlatScene:
             ni[A.NI_AABB] = 1
             nf[A.NF_AABB:A.NF_AABB + 6] = [float(v) for v in comp.bbox]
             children = [t for t in (self._visit(child, in_group=True) for child in comp.components) if t is not None]
+            if len(children) >= self.GRID_MIN_CHILDREN:
+                self._grid(ni, children)
             if len(children) >= self.BVH_MIN_CHILDREN:
                 children = self._wrap_runs(children)
             return ni, nf, children

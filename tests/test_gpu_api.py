@@ -247,7 +247,7 @@ def test_bench_line_contract_small():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     run = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--rays", "200000", "--steps", "3", "--warmup", "3",
-                          "--e2e-steps", "1", "--cpu-rays", "500"], capture_output=True, text=True, cwd=root, timeout=600)
+                          "--e2e-steps", "1", "--cpu-rays", "500", "--flag-rays", "20000"], capture_output=True, text=True, cwd=root, timeout=900)
     assert run.returncode == 0, run.stderr[-2000:]
     lines = [l for l in run.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -260,6 +260,13 @@ def test_bench_line_contract_small():
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and 0 < d["roofline"]["frac"] < 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["config"]["interactions_per_step_per_gpu"] == 4 * 200000
+    # the other BASELINE configs ride in the same line, each with its own device value, e2e, roofline and CPU baseline
+    assert set(d["workloads"]) == {"c3_doublets_16wl", "c4_cavity_4000", "c5_ripa_64"}
+    for name, w in d["workloads"].items():
+        assert w["value"] > 1e8 and w["e2e"]["value"] > 1e6 and 0 < w["roofline"]["frac"] < 1.5, name
+        assert w["cpu_baseline"]["value"] > 0 and w["config"]["rays_per_gpu"] == 200000, name
+    assert d["workloads"]["c4_cavity_4000"]["config"]["interactions_per_step_per_gpu"] == 4001 * 200000
+    assert d["roofline_hbm"]["frac"] < 1 and d["roofline"]["bound"] == "fp64" and d["fp64_peak"]["tflops"] > 10
 
 
 def test_component_interact_single_pop_on_device():

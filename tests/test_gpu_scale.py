@@ -195,3 +195,53 @@ def test_one_ray_whose_generation_outgrows_64_live_rays(engine):
     table.add_components(comps)
     ray = ob.Ray([-1, 0.01, 0.02], [1, 0, 0], wavelength=780e-7, w0=61e-4)
     assert len(table.ray_tracing(ray)) == 2000
+
+
+@pytest.mark.parametrize("case", ["mma_oblique", "mla_dmd", "ripa", "mma_small"])
+def test_lattice_window_walk_equals_reference_walk(engine, case, monkeypatch):
+    """OPTB_G_GRID groups (flatten._grid): the device lists the children inside the ray's lattice window instead of
+    descending the box hierarchy. The oracle ignores the descriptor and box-tests every child like the reference
+    (component_group.py:104-115): same segments, same monitor rows, same leaf-test count. Rays come from all
+    directions, including nearly in-plane ones (window refused -> hierarchy) and axis-parallel ones (parallel-axis
+    branch of the slab test -> hierarchy)."""
+    import optable_b200 as ob
+    from optable_b200 import _abi as A
+    from optable_b200.flatten import FlatScene
+
+    monkeypatch.setattr(FlatScene, "GRID_MIN_CHILDREN", 6)
+    rng = np.random.default_rng(11)
+    if case == "mma_oblique":
+        mma = ob.MMA(origin=[5, 0, 0], N=(12, 9), pitch=0.3, roc=2.0, n=1.5, thickness=0.2, reflectivity=0.9,
+                     transmission=0.1, shifty_z=0.02).RotZ(0.3).RotY(-0.2)
+        sc = scenes.Scene([mma, ob.Mirror([-3, 0, 0], radius=6)], [], [ob.Monitor([2, 0, 0], 8, 8)])
+        n = 30_000
+        o = np.column_stack([rng.uniform(-2, 4, n), rng.uniform(-3, 3, n), rng.uniform(-3, 3, n)])
+        tgt = np.array([5.0, 0, 0]) + np.column_stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-2.5, 2.5, n), rng.uniform(-2, 2, n)])
+        d = tgt - o
+        d[: n // 20] = [0.0, 1.0, 0.0]           # axis-parallel rays along the array
+        d[n // 20: n // 10, 0] *= 1e-4           # nearly in-plane
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        arrs = scenes.ray_arrays(n, [0, 0, 0], [0, 0, 0], [1, 0, 0], [0, 0, 0])
+        for k, ax in enumerate("xyz"):
+            arrs["o" + ax], arrs["d" + ax] = np.ascontiguousarray(o[:, k]), np.ascontiguousarray(d[:, k])
+        limit = 12
+    elif case == "mla_dmd":
+        mla = ob.MLA([4, 0, 0], N=(7, 6), pitch=0.5, focal_length=3.0, radius=0.3)
+        dmd = ob.DMD([8, 0, 0], N=(8, 8), pitch=0.4, tilt_angle=0.2)
+        sc = scenes.Scene([mla, dmd], [], [ob.Monitor([0.5, 0, 0], 6, 6)])
+        arrs = scenes.ray_arrays(30_000, [0, 0, 0], [0, 1.6, 1.4], [1, 0, 0], [0, 0.05, 0.05])
+        limit = 10
+    elif case == "ripa":
+        sc = scenes.ripa(ob, n_rays=0)
+        import bench
+
+        arrs = bench.make_bundle(20_000, 0, "c5_ripa_64").materialise()
+        limit = 40
+    else:
+        sc = scenes.mma_small(ob)
+        arrs = scenes.ray_arrays(20_000, [0, 0, 0], [0, 0.1, 0.03], [1, 0, 0], [0, 0.02, 0.02])
+        limit = 60
+    flat = FlatScene(sc.components, sc.monitors)
+    assert (flat.node_i[:, A.NI_GEOM] == A.G_GRID).any(), "the scene was meant to contain a lattice group"
+    got, errs = _both(engine, sc, arrs, limit=limit, max_live=max(40 * len(arrs["ox"]), 1 << 20))
+    assert int(got["counters"][A.C_INTERACTIONS]) > len(arrs["ox"]) // 4
