@@ -341,6 +341,25 @@ int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays,
 int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays,
                     const optb_params* params, optb_result* out);
 
+/* ---- multi-GPU monitor merge -----------------------------------------------------------------------
+ * The path shards without a data-path collective: every rank (one process per GPU, one ctx each) traces its own block
+ * of the initial rays against its own copy of the scene. The only exchange is the merge of the monitors at the end,
+ * which the reference -- single process -- gets for free from Monitor.record appending to one list (monitor.py:183-193):
+ * an all-reduce (sum) of the histograms and counters over NCCL. Python hosts use torch.distributed
+ * (optable_b200/dist.py); these entry points give a C host the same thing. NCCL is loaded at run time (dlopen of
+ * $OPTB_NCCL_LIB, else the libnccl.so.2 already in the process or on the loader path): the library has no link-time
+ * dependency on it.
+ *   optb_comm_unique_id   rank 0: fills the 128-byte ncclUniqueId to hand to the other ranks (any transport)
+ *   optb_comm_init        all ranks: joins the communicator (collective call)
+ *   optb_monitor_merge    all ranks: in-place sum over ranks of hist_y [n_monitors][30], hist_yz [n_monitors][30][30]
+ *                         and counters [OPTB_C_COUNT] (device pointers; any may be NULL; the status word is OR-ed,
+ *                         OPTB_C_GENERATIONS takes the maximum), enqueued on `stream`
+ *   optb_comm_destroy     leaves the communicator                                                                  */
+int optb_comm_unique_id(optb_ctx* ctx, void* id128);
+int optb_comm_init(optb_ctx* ctx, const void* id128, int rank, int nranks);
+int optb_monitor_merge(optb_ctx* ctx, int64_t* hist_y, int64_t* hist_yz, int n_monitors, int64_t* counters, void* stream);
+int optb_comm_destroy(optb_ctx* ctx);
+
 /* Device micro-benchmarks used for the roofline denominators: returns achieved FP64 FMA
  * TFLOP/s (dfma) measured with CUDA events.                                            */
 int optb_measure_fp64_peak(optb_ctx* ctx, double* tflops_out);

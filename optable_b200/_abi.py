@@ -83,4 +83,5 @@ EXPORTED_SYMBOLS = (
     "optb_abi_version", "optb_ctx_create", "optb_ctx_destroy", "optb_last_error",
     "optb_scene_upload", "optb_scene_destroy", "optb_workspace_bytes", "optb_trace",
     "optb_trace_host", "optb_measure_fp64_peak",
+    "optb_comm_unique_id", "optb_comm_init", "optb_monitor_merge", "optb_comm_destroy",
 )

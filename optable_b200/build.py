@@ -12,7 +12,7 @@ SOURCES = ["optb.cu"]
 DEPS = ["optb.cu", "optb_device.cuh", os.path.join("..", "..", "include", "optb.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

@@ -61,6 +61,14 @@ class RayBundle:
         b.has_q = bool(w0)
         return b
 
+    def slice(self, lo: int, hi: int) -> "RayBundle":
+        """Rays [lo, hi) as a bundle of their own (broadcast columns stay single values; views, no copies)."""
+        cols = {k: (c if c is None or np.asarray(c).size == 1 else c[lo:hi]) for k, c in self.columns.items()}
+        b = RayBundle(cols, hi - lo)
+        if hasattr(self, "has_q"):
+            b.has_q = self.has_q
+        return b
+
     def materialise(self) -> dict:
         """Full-length numpy columns (+ flags / family) for the oracle or for object-level comparisons."""
         out = {}

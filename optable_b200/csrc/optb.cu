@@ -12,6 +12,7 @@
 //   sort_prep + cub radix sort    processing order of a generation by coherence key (storage order stays BFS).
 // Segments and monitor rows are appended with warp-aggregated atomics and carry their (root, pop) key.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <stddef.h>
 #include <stdio.h>
@@ -790,6 +791,8 @@ struct optb_ctx {
   struct { unsigned char* p; size_t cap; } pool[8];
   // live-ray budget per initial ray that the last splitting optb_trace_host call needed (its grow loop starts there)
   int64_t live_per_ray_hint;
+  // NCCL communicator for optb_monitor_merge (library loaded at run time)
+  void* nccl_lib; void* nccl_comm; int comm_rank, comm_size; long long* d_merge;  // d_merge: device scratch of the merge
 };
 
 struct optb_scene {
@@ -812,6 +815,7 @@ static int fail(optb_ctx* ctx, int code, const char* what, cudaError_t e = cudaS
 #define CK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(ctx, -10, what, e__); } while (0)
 
 extern "C" int optb_abi_version(void) { return OPTB_ABI_VERSION; }
+extern "C" int optb_comm_destroy(optb_ctx* ctx);
 
 extern "C" int optb_ctx_create(int device, optb_ctx** out) {
   if (!out) return -1;
@@ -841,6 +845,7 @@ extern "C" int optb_ctx_create(int device, optb_ctx** out) {
 extern "C" int optb_ctx_destroy(optb_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
+  optb_comm_destroy(ctx);
   if (ctx->arena) cudaFree(ctx->arena);
   for (auto& b : ctx->pool) if (b.p) cudaFree(b.p);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -1578,5 +1583,123 @@ extern "C" int optb_measure_fp64_peak(optb_ctx* ctx, double* tflops_out) {
   if (e != cudaSuccess) return fail(ctx, -10, "dfma kernel", e);
   double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
   *tflops_out = flops / (best * 1e-3) / 1e12;
+  return 0;
+}
+
+
+// ---- multi-GPU monitor merge over NCCL (loaded at run time: no link-time dependency) ------------------------------
+namespace {
+// the few NCCL entry points used, with the ABI of nccl.h (ncclResult_t = int, ncclUniqueId = 128 bytes by value)
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  int (*GetUniqueId)(NcclId*);
+  int (*CommInitRank)(void**, int, NcclId, int);
+  int (*CommDestroy)(void*);
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+  const char* (*GetErrorString)(int);
+};
+constexpr int kNcclInt64 = 4, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t / ncclRedOp_t values of nccl.h
+NcclApi g_nccl;
+void* g_nccl_handle = nullptr;
+
+int load_nccl(optb_ctx* ctx) {
+  if (g_nccl_handle) return 0;
+  void* h = nullptr;
+  if (const char* p = getenv("OPTB_NCCL_LIB")) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // already in the process (e.g. torch's)
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(ctx, -11, "NCCL not found: set OPTB_NCCL_LIB to libnccl.so.2");
+  NcclApi a;
+  a.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+  a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  a.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+  a.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+  a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GroupStart || !a.GroupEnd)
+    return fail(ctx, -11, "NCCL library lacks an expected symbol");
+  g_nccl = a; g_nccl_handle = h;
+  return 0;
+}
+int nccl_fail(optb_ctx* ctx, const char* what, int rc) {
+  snprintf(ctx->err, sizeof ctx->err, "%s: NCCL error %d (%s)", what, rc, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return -11;
+}
+
+// status word -> one slot per bit (so that a sum over ranks is an OR), generations -> their own slot (maximum)
+constexpr int kMergeBits = 16;
+__global__ void merge_prep_kernel(long long* counters, long long* scratch) {
+  const int k = threadIdx.x;
+  if (k < kMergeBits) scratch[k] = (counters[OPTB_C_STATUS] >> k) & 1;
+  if (k == kMergeBits) scratch[kMergeBits] = counters[OPTB_C_GENERATIONS];
+  __syncthreads();
+  if (k == 0) { counters[OPTB_C_STATUS] = 0; counters[OPTB_C_GENERATIONS] = 0; }
+}
+__global__ void merge_post_kernel(long long* counters, const long long* scratch) {
+  if (threadIdx.x == 0) {
+    long long st = 0;
+    for (int k = 0; k < kMergeBits; k++) if (scratch[k] > 0) st |= 1ll << k;
+    counters[OPTB_C_STATUS] = st;
+    counters[OPTB_C_GENERATIONS] = scratch[kMergeBits];
+  }
+}
+}  // namespace
+
+extern "C" int optb_comm_unique_id(optb_ctx* ctx, void* id128) {
+  if (!ctx || !id128) return -1;
+  if (int rc = load_nccl(ctx)) return rc;
+  NcclId id;
+  if (int rc = g_nccl.GetUniqueId(&id)) return nccl_fail(ctx, "ncclGetUniqueId", rc);
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+extern "C" int optb_comm_init(optb_ctx* ctx, const void* id128, int rank, int nranks) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return -1;
+  if (ctx->nccl_comm) return fail(ctx, -7, "communicator already initialised");
+  if (int rc = load_nccl(ctx)) return rc;
+  cudaSetDevice(ctx->device);
+  NcclId id;
+  memcpy(&id, id128, sizeof id);
+  void* comm = nullptr;
+  if (int rc = g_nccl.CommInitRank(&comm, nranks, id, rank)) return nccl_fail(ctx, "ncclCommInitRank", rc);
+  CK(cudaMalloc((void**)&ctx->d_merge, sizeof(long long) * (kMergeBits + 1)), "cudaMalloc(merge scratch)");
+  ctx->nccl_comm = comm; ctx->comm_rank = rank; ctx->comm_size = nranks;
+  return 0;
+}
+
+extern "C" int optb_monitor_merge(optb_ctx* ctx, int64_t* hist_y, int64_t* hist_yz, int n_monitors, int64_t* counters,
+                                  void* stream_v) {
+  if (!ctx || n_monitors < 0) return -1;
+  if (!ctx->nccl_comm) return fail(ctx, -7, "optb_monitor_merge: call optb_comm_init first");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream_v;
+  if (ctx->comm_size == 1) return 0;
+  if (counters) merge_prep_kernel<<<1, 32, 0, st>>>((long long*)counters, ctx->d_merge);
+  int rc = g_nccl.GroupStart();
+  if (!rc && hist_y && n_monitors) rc = g_nccl.AllReduce(hist_y, hist_y, (size_t)n_monitors * OPTB_HIST_BINS, kNcclInt64, kNcclSum, ctx->nccl_comm, st);
+  if (!rc && hist_yz && n_monitors) rc = g_nccl.AllReduce(hist_yz, hist_yz, (size_t)n_monitors * OPTB_HIST_BINS * OPTB_HIST_BINS, kNcclInt64, kNcclSum, ctx->nccl_comm, st);
+  if (!rc && counters) rc = g_nccl.AllReduce(counters, counters, OPTB_C_COUNT, kNcclInt64, kNcclSum, ctx->nccl_comm, st);
+  if (!rc && counters) rc = g_nccl.AllReduce(ctx->d_merge, ctx->d_merge, kMergeBits, kNcclInt64, kNcclSum, ctx->nccl_comm, st);
+  if (!rc && counters) rc = g_nccl.AllReduce(ctx->d_merge + kMergeBits, ctx->d_merge + kMergeBits, 1, kNcclInt64, kNcclMax, ctx->nccl_comm, st);
+  int rc2 = g_nccl.GroupEnd();
+  if (rc || rc2) return nccl_fail(ctx, "ncclAllReduce", rc ? rc : rc2);
+  if (counters) merge_post_kernel<<<1, 32, 0, st>>>((long long*)counters, ctx->d_merge);
+  CK(cudaGetLastError(), "merge kernels");
+  return 0;
+}
+
+extern "C" int optb_comm_destroy(optb_ctx* ctx) {
+  if (!ctx) return -1;
+  if (ctx->nccl_comm) {
+    cudaSetDevice(ctx->device);
+    g_nccl.CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  if (ctx->d_merge) { cudaFree(ctx->d_merge); ctx->d_merge = nullptr; }
   return 0;
 }

@@ -74,3 +74,73 @@ def gather_rows(columns: dict, n_rows: int, root_offset: int = 0, group=None):
         dist.all_gather(parts, padded, group=group)
         out[k] = torch.cat([p[:c] for p, c in zip(parts, counts)])
     return out
+
+
+def merge_counters(counters, group=None):
+    """Sum over ranks of the OPTB_C_* counters of one sharded trace (numpy int64 array or tensor); the status word is
+    a bit mask and is OR-ed. Returns a numpy array."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _abi as A
+
+    c = torch.as_tensor(np.asarray(counters, dtype=np.int64)).clone()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return c.numpy()
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    bits = torch.tensor([(int(c[A.C_STATUS]) >> k) & 1 for k in range(16)], dtype=torch.int64)
+    c[A.C_STATUS] = 0
+    gens = c[A.C_GENERATIONS].clone()
+    both = torch.cat([c, bits, gens.reshape(1)]).to(dev)
+    dist.all_reduce(both, group=group)
+    mx = gens.reshape(1).to(dev)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    both = both.cpu()
+    out = both[:len(c)].clone()
+    out[A.C_STATUS] = sum((1 << k) for k in range(16) if int(both[len(c) + k]) > 0)
+    out[A.C_GENERATIONS] = int(mx.item())  # generations run side by side on the ranks: the longest shard counts
+    return out.numpy()
+
+
+def trace_sharded(table, bundle, perfomance_limit=None, group=None, gather=False, record_hits=True, record_hist=True,
+                  engine=None, tracer=None, **kw):
+    """Multi-GPU form of `OpticalTable.trace_bundle`: rank r of `group` traces the contiguous block
+    [lo, hi) = shard_bounds(bundle.n, r, world) of the initial rays on its own GPU against its own replica of the
+    scene tables; no data-path collective. The only exchange is the monitor merge at the end: all-reduce of the
+    histograms and of the counters and, with `gather=True`, a gather-v of the monitor row columns so that every
+    rank holds all rows (concatenated in rank order = initial-ray block order). Row keys are global (`hit_root` /
+    `hit_key` count from ray 0 of the whole bundle).
+
+    Returns the dict of `trace_bundle` with merged `hist_y` / `hist_yz` / `counters`, plus `counters_local` and
+    `shard` = (lo, hi). Without an initialised process group it is `trace_bundle` on the whole bundle.
+    `tracer(table, bundle, perfomance_limit, record_hits=, record_hist=, engine=, **kw)` defaults to the CUDA
+    `bundle.trace_bundle`; the CPU tests of this module pass a stand-in."""
+    import torch.distributed as dist
+
+    from . import _abi as A
+
+    on = dist.is_initialized()
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+    lo, hi = shard_bounds(bundle.n, rank, world)
+    if tracer is None:
+        from .bundle import trace_bundle as tracer
+    res = tracer(table, bundle.slice(lo, hi), perfomance_limit, record_hits=record_hits, record_hist=record_hist,
+                 engine=engine, **kw)
+    rows = {k: v for k, v in res.items() if k.startswith("hit_")}
+    n_rows = int(res["counters"][A.C_HITS]) if record_hits else 0
+    if lo:
+        if "hit_root" in rows:
+            rows["hit_root"] = rows["hit_root"] + int(lo)     # uint32 bit pattern in int32: wraps like unsigned
+        if "hit_key" in rows:
+            rows["hit_key"] = rows["hit_key"] + (int(lo) << 32)
+    out = dict(res)
+    out["counters_local"] = np.asarray(res["counters"]).copy()
+    out["shard"] = (lo, hi)
+    if on and world > 1:
+        if record_hist:
+            merge_histograms(res["hist_y"], res["hist_yz"], group)
+        out["counters"] = merge_counters(res["counters"], group)
+        if gather and record_hits:
+            rows = gather_rows(rows, n_rows, 0, group)
+    out.update(rows)
+    return out

@@ -386,8 +386,14 @@ class OpticalTable:
         print(f"Exporting components to {filename} ...")
         write_csv(filename, self.gather_components(avoid_flatten_classname, ignore_classname))
 
-    def trace_bundle(self, bundle, perfomance_limit=None, **kw):
-        """Tensor entry point: see optable_b200.bundle.trace_bundle."""
+    def trace_bundle(self, bundle, perfomance_limit=None, group=None, gather=False, **kw):
+        """Tensor entry point: see optable_b200.bundle.trace_bundle. Under an initialised torch.distributed process
+        group (one rank per GPU) pass `group=` (or `group=True` for the default group): the bundle is sharded over
+        the ranks and the monitors are merged (optable_b200.dist.trace_sharded)."""
+        if group is not None and group is not False:
+            from .dist import trace_sharded
+
+            return trace_sharded(self, bundle, perfomance_limit, group=None if group is True else group, gather=gather, **kw)
         from .bundle import trace_bundle
 
         return trace_bundle(self, bundle, perfomance_limit, **kw)

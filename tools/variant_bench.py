@@ -26,13 +26,14 @@ def child(args):
     engine = Engine.get(0)
     out = {}
     for wl in args.workloads.split(","):
-        flat = bench.build_scene(wl)
-        wprm = bench._workloads()[wl][2]
-        n = int(wprm["rays"] * args.scale)
-        bundle = bench.make_bundle(n, 0, wl)
+        w = bench.workloads()[wl]
+        flat = w.flat()
+        n = int((args.rays or min(w.rays_per_gpu, 10_000_000 if w.max_live == 0 else 1_000_000)) * args.scale)
+        bundle = w.bundle(n, 0)
         rays_dev = bundle.to_torch(device="cuda:0")
-        dt = DeviceTrace(engine, flat, n, n * wprm["rows_per_ray"] + 1024, record_hist=True, max_trace_num=wprm["max_trace_num"])
-        live = wprm.get("max_live", 0) * n or None
+        dt = DeviceTrace(engine, flat, n, n * w.rows_per_ray + 1024, record_hist=True, max_trace_num=w.max_trace_num,
+                         hit_columns=bench.E2E_COLUMNS)
+        live = w.max_live * n or None
         for _ in range(3):
             dt.run(rays_dev, live)
         torch.cuda.synchronize()
@@ -46,7 +47,8 @@ def child(args):
             torch.cuda.synchronize()
             ms.append(e0.elapsed_time(e1))
         out[wl] = {"ms": float(np.median(ms)), "min_ms": float(min(ms)), "interactions": int(cnt[A.C_INTERACTIONS]),
-                   "hits": int(cnt[A.C_HITS]), "tests": int(cnt[A.C_TESTS]), "status": int(cnt[A.C_STATUS])}
+                   "hits": int(cnt[A.C_HITS]), "tests": int(cnt[A.C_TESTS]), "status": int(cnt[A.C_STATUS]),
+                   "box_tests": int(cnt[A.C_BOX_TESTS]) if len(cnt) > 9 else None, "launches": int(cnt[A.C_LAUNCHES])}
         del dt, rays_dev
         engine._workspace = None
         torch.cuda.empty_cache()
@@ -59,6 +61,7 @@ def main():
     ap.add_argument("--workloads", default="c2_4f_telescope,c3_doublets_16wl,c4_cavity_4000,c5_ripa_64")
     ap.add_argument("--steps", type=int, default=7)
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--rays", type=int, default=0)
     ap.add_argument("--child", action="store_true")
     args = ap.parse_args()
     if args.child:
@@ -69,7 +72,7 @@ def main():
         if v != "intree":
             env["OPTB_LIB_PATH"] = os.path.join(ROOT, "build_variants", f"liboptb_{v}.so")
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--workloads", args.workloads, "--steps", str(args.steps),
-                            "--scale", str(args.scale)], env=env, capture_output=True, text=True)
+                            "--scale", str(args.scale), "--rays", str(args.rays)], env=env, capture_output=True, text=True)
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
         if not line:
             print(f"{v}: FAILED\n{r.stdout[-2000:]}\n{r.stderr[-3000:]}")
