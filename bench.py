@@ -39,8 +39,9 @@ RAY_RECORD_BYTES = 104  # 12 fp64 + root + flags per ray
 # OPTB_C_TESTS_CURVED, OPTB_C_BOX_TESTS), so nothing here is pasted from a profile.
 FLOPS_PLANAR, FLOPS_CURVED, FLOPS_BOX, FLOPS_INTERACT = 55, 200, 25, 180
 # default monitor row of the end-to-end leg = what Monitor._data_raw holds (monitor.py:15-20): P_local, intensity, t
-# + the (monitor, root, pop) key = 52 B; direction and q of the segment are opt-in columns (--e2e-columns all: 92 B)
-E2E_COLUMNS = ("hit_monitor", "hit_root", "hit_pop", "hit_px", "hit_py", "hit_pz", "hit_intensity", "hit_t")
+# + the packed (root, monitor, pop) key = 48 B; direction and q of the segment are opt-in columns
+# (--e2e-columns all: 92 B with the key as three columns)
+E2E_COLUMNS = ("hit_key", "hit_px", "hit_py", "hit_pz", "hit_intensity", "hit_t")
 
 
 def workloads():
@@ -454,6 +455,8 @@ def run_e2e(args, D, engine, dt, bundle, n, hit_cap, hit_columns, hit_dtypes, ro
     rows_gb = hits_per_step * row_bytes / 1e9
     e2e = None
     if rows_gb <= args.e2e_max_row_gb:
+        prm_rows = copy.copy(dt.prm)
+        prm_rows.sorted_rows = 1  # rows arrive in (root, monitor, pop) order: what Monitor._data_raw would hold
         res = A.Result()
         res.seg_capacity, res.hit_capacity = 0, hit_cap
         host_out = {}
@@ -461,10 +464,14 @@ def run_e2e(args, D, engine, dt, bundle, n, hit_cap, hit_columns, hit_dtypes, ro
             host_out[k] = torch.empty(hit_cap, dtype=hit_dtypes[k]).pin_memory()
             setattr(res, k, host_out[k].data_ptr())
         res.hist_y, res.hist_yz, res.counters = hy.data_ptr(), hyz.data_ptr(), hc.data_ptr()
-        v = timed(res, dt.prm)
+        v = timed(res, prm_rows)
+        keys = host_out["hit_key"][:hits_per_step].numpy() if "hit_key" in host_out else None
+        if keys is not None:
+            ku = keys.view(np.uint64)
+            assert bool((ku[1:] >= ku[:-1]).all()), "rows not in reference order"
         e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(hits_per_step * row_bytes + small),
                "steps": e2e_steps, "api": "optb_trace_host (C ABI, pinned host buffers)",
-               "result": f"every monitor row ({row_bytes} B: {', '.join(c[4:] for c in hit_columns)}) + histograms + counters",
+               "result": f"every monitor row ({row_bytes} B: {', '.join(c[4:] for c in hit_columns)}) in (root, monitor, pop) order + histograms + counters",
                "input_encoding": "%d real fp64 columns + %d broadcast (one value for all rays)" % (
                    sum(1 for v in host.values() if v.numel() > 1), sum(1 for v in host.values() if v.numel() == 1))}
         del host_out, res

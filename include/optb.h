@@ -212,7 +212,10 @@ typedef struct optb_params {
   int32_t flag_ambiguity; /* 1: evaluate the ambiguity mask of SURVEY A.9 at every pop (OPTB_AMB_* bits OR-ed per
                              initial ray into optb_result.root_flags, flagged roots counted in OPTB_C_FLAGGED).
                              A diagnostics mode: it runs the general kernel variant.                        */
-  int32_t reserved;
+  int32_t sorted_rows;    /* optb_trace_host only: 1 = deliver the monitor rows in (root, monitor, pop) order and the
+                             segments in (root, pop) order -- the order Monitor.record / OpticalTable.rays have after
+                             the reference traced the initial rays one after another -- instead of device append
+                             order. Sorted on the device (optb_sort_rows) before the copy back.                  */
 } optb_params;
 
 /* Ambiguity bits (the "stated epsilon" of the parity bar): set for an initial ray when, at some pop,
@@ -340,6 +343,15 @@ int optb_trace(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays,
  * the filled prefix of every requested result array back. Used for end-to-end timing.         */
 int optb_trace_host(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays,
                     const optb_params* params, optb_result* out);
+
+/* Put the first n_seg segment rows of `res` into (root, pop) order and its first n_hit monitor rows into
+ * (root, monitor, pop) order, in place: what a caller of optb_trace does once it has read the counters (rows are
+ * appended in device order). DEVICE pointers; NULL columns are skipped; the key columns (seg_root + seg_pop;
+ * hit_key, or hit_root + hit_pop + hit_monitor) must be present. Needs pop < 2^24 and <= 256 monitors (-7 otherwise).
+ * workspace: optb_sort_workspace_bytes(max(n_seg, n_hit)) bytes of device memory.                                */
+int64_t optb_sort_workspace_bytes(int64_t n_rows);
+int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_seg, int64_t n_hit,
+                   void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- multi-GPU monitor merge -----------------------------------------------------------------------
  * The path shards without a data-path collective: every rank (one process per GPU, one ctx each) traces its own block

@@ -56,7 +56,7 @@ class Params(C.Structure):
         ("max_trace_num", C.c_int64), ("unit", C.c_double),
         ("record_segments", C.c_int32), ("record_hits", C.c_int32), ("record_hist", C.c_int32),
         ("chain_len", C.c_int32), ("n_families", C.c_int32), ("caps_slack", C.c_int32),
-        ("flag_ambiguity", C.c_int32), ("reserved", C.c_int32),
+        ("flag_ambiguity", C.c_int32), ("sorted_rows", C.c_int32),
     ]
 
 
@@ -83,5 +83,6 @@ EXPORTED_SYMBOLS = (
     "optb_abi_version", "optb_ctx_create", "optb_ctx_destroy", "optb_last_error",
     "optb_scene_upload", "optb_scene_destroy", "optb_workspace_bytes", "optb_trace",
     "optb_trace_host", "optb_measure_fp64_peak",
+    "optb_sort_workspace_bytes", "optb_sort_rows",
     "optb_comm_unique_id", "optb_comm_init", "optb_monitor_merge", "optb_comm_destroy",
 )

@@ -42,6 +42,9 @@ def lib():
                                  C.c_void_p, C.c_int64, C.c_void_p]
         L.optb_trace_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.Rays), C.POINTER(A.Params), C.POINTER(A.Result)]
         L.optb_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.optb_sort_workspace_bytes.restype = C.c_int64
+        L.optb_sort_workspace_bytes.argtypes = [C.c_int64]
+        L.optb_sort_rows.argtypes = [C.c_void_p, C.POINTER(A.Result), C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         if L.optb_abi_version() != A.ABI_VERSION:
             raise BackendError("liboptb.so ABI version does not match optable_b200._abi")
         _lib = L
@@ -312,9 +315,8 @@ class Engine:
             presorted = False
         else:
             # large results: put the rows into reference order on the device (one 64-bit key per row), then copy
-            dev_t = {k: (v[:trim[k]] if k in trim else v) for k, v in t.items()}
-            presorted = self._sort_rows_on_device(dev_t, nseg, nhit, int(max_trace_num), flat.n_monitors)
-            out = {k: v.cpu().numpy() for k, v in dev_t.items()}
+            presorted = self._sort_rows_on_device(res, nseg, nhit, int(max_trace_num), flat.n_monitors)
+            out = {k: (v[:trim[k]] if k in trim else v).cpu().numpy() for k, v in t.items()}
         for k in A.SEG_U32 + A.HIT_U32:
             out[k] = out[k].view(np.uint32)
         self._raise_status(out["counters"])
@@ -330,26 +332,19 @@ class Engine:
                 out[k] = out[k][order]
         return out
 
-    def _sort_rows_on_device(self, t, nseg, nhit, max_trace_num, n_monitors):
-        """Reorder the row columns in `t` (CUDA tensors) to (root, pop) / (root, monitor, pop). The key is packed
-        into one int64 (root < 2^32, pop < max_trace_num); returns False when it would not fit (caller sorts on
-        the host)."""
-        torch = self.torch
-        pop_bits = max(int(max_trace_num), 1).bit_length()
-        mon_bits = max(int(n_monitors), 1).bit_length()
-        if 32 + pop_bits + mon_bits > 63:
+    def _sort_rows_on_device(self, res, nseg, nhit, max_trace_num, n_monitors):
+        """Reorder the row columns of `res` (device buffers) to (root, pop) / (root, monitor, pop) with the library's
+        own sort (optb_sort_rows: one packed 64-bit key per row + a gather per column). Returns False when the key
+        would not fit (pop >= 2^24 or > 256 monitors): the caller then sorts on the host."""
+        if int(max_trace_num) > (1 << 24) or int(n_monitors) > 256:
             return False
-        u32 = lambda x: x.to(torch.int64) & 0xFFFFFFFF
-        if nseg:
-            key = (u32(t["seg_root"]) << pop_bits) | u32(t["seg_pop"])
-            order = torch.argsort(key)
-            for k in A.SEG_F64 + A.SEG_U32 + A.SEG_I32:
-                t[k] = t[k][order]
-        if nhit:
-            key = (((u32(t["hit_root"]) << mon_bits) | t["hit_monitor"].to(torch.int64)) << pop_bits) | u32(t["hit_pop"])
-            order = torch.argsort(key)
-            for k in A.HIT_I32 + A.HIT_U32 + A.HIT_F64:
-                t[k] = t[k][order]
+        n = max(int(nseg), int(nhit))
+        if n <= 1:
+            return True
+        nbytes = lib().optb_sort_workspace_bytes(n)
+        ws = self._ws(nbytes)
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self._check(lib().optb_sort_rows(self._ctx, C.byref(res), int(nseg), int(nhit), ws.data_ptr(), int(ws.numel()), C.c_void_p(st)))
         return True
 
     @staticmethod

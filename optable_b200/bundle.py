@@ -147,19 +147,31 @@ class DeviceTrace:
 
 
 def trace_bundle(table, bundle: RayBundle, perfomance_limit=None, record_hits=True, record_hist=False,
-                 hit_capacity=None, engine=None):
+                 hit_capacity=None, engine=None, max_live=None, hit_columns=HIT_COLUMNS_ALL):
     """Trace a RayBundle through `table` entirely on the device; returns a dict of CUDA tensors (hit columns
     trimmed to the rows produced, histograms, counters as numpy). Rows are in device append order and carry
     their (root, pop) key."""
     from .backend import Engine
-    from .flatten import FlatScene, trace_cap
+    from .flatten import FlatScene, batch_wavelengths_m, trace_cap
 
     engine = engine or Engine.get()
-    flat = FlatScene(table.components, table.monitors)
+    wl = bundle.columns.get("wavelength")
+    flat = FlatScene(table.components, table.monitors,
+                     wavelengths_m=None if wl is None else batch_wavelengths_m(wl, getattr(table, "unit", 1e-2)))
     cap = int(hit_capacity if hit_capacity is not None else bundle.n * max(flat.n_monitors, 1) * 2) if record_hits else 0
-    dt = DeviceTrace(engine, flat, bundle.n, cap, max_trace_num=trace_cap(perfomance_limit), record_hist=record_hist)
-    dt.run(bundle.to_torch(device=f"cuda:{engine.device}"))
-    cnt = dt.counters()
+    limit = trace_cap(perfomance_limit)
+    dt = DeviceTrace(engine, flat, bundle.n, cap, max_trace_num=limit, record_hist=record_hist, hit_columns=hit_columns)
+    rays_t = bundle.to_torch(device=f"cuda:{engine.device}")
+    # live-ray budget of a splitting scene: grow on overflow towards the bound 2 n max_trace_num (a root pops at most
+    # max_trace_num rays and each pop queues at most two)
+    live, bound = max_live, max(2 * bundle.n * max(limit, 1), 1024)
+    while True:
+        dt.run(rays_t, live)
+        cnt = dt.counters()
+        cur = live if live is not None else max(4 * bundle.n, 1024)
+        if not int(cnt[A.C_STATUS]) & A.ST_WORK_OVERFLOW or cur >= bound:
+            break
+        live = min(4 * cur, bound)
     engine._raise_status(cnt)
     nh = int(cnt[A.C_HITS]) if record_hits else 0
     out = {k: dt.t[k][:nh] for k in dt.hit_columns}

@@ -816,6 +816,9 @@ static int fail(optb_ctx* ctx, int code, const char* what, cudaError_t e = cudaS
 
 extern "C" int optb_abi_version(void) { return OPTB_ABI_VERSION; }
 extern "C" int optb_comm_destroy(optb_ctx* ctx);
+extern "C" int64_t optb_sort_workspace_bytes(int64_t n_rows);
+extern "C" int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_seg, int64_t n_hit, void* workspace,
+                              int64_t workspace_bytes, void* stream_v);
 
 extern "C" int optb_ctx_create(int device, optb_ctx** out) {
   if (!out) return -1;
@@ -1326,8 +1329,10 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     CK(cudaMallocHost((void**)&ctx->h_chunk, sizeof(unsigned long long) * OPTB_C_COUNT * nch), "pinned counters");
     ctx->h_chunk_n = nch;
   }
-  size_t need = 256 * 128 + (size_t)n * (8 * 13 + 8) + 2 * ((size_t)cseg * (13 * 8 + 16) + (size_t)chit * (10 * 8 + 12)) +
-                (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 8 + 2 * (64 * 8 + (size_t)wsb) + 4096;
+  const int64_t sortb = prm->sorted_rows ? optb_sort_workspace_bytes(std::max(cseg, chit)) : 0;
+  size_t need = 256 * 128 + (size_t)n * (8 * 13 + 8) + 2 * ((size_t)cseg * (13 * 8 + 16) + (size_t)chit * (10 * 8 + 12 + 8)) +
+                (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 8 + 2 * (64 * 8 + (size_t)wsb) +
+                (size_t)sortb + 4096;
   if (ctx->arena_bytes < need) {
     if (ctx->arena) cudaFree(ctx->arena);
     ctx->arena = nullptr; ctx->arena_bytes = 0;
@@ -1367,6 +1372,7 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     add(OPTB_FIELD(seg_pop), 4, cseg, 0); add(OPTB_FIELD(seg_leaf), 4, cseg, 0);
     add(OPTB_FIELD(hit_monitor), 4, chit, 1); add(OPTB_FIELD(hit_root), 4, chit, 1); add(OPTB_FIELD(hit_pop), 4, chit, 1);
     for (int f = 0; f < 10; f++) add(hit0 + 8 * f, hit_h[f], 8, chit, 1);
+    add(OPTB_FIELD(hit_key), 8, chit, 1);
   }
 #undef OPTB_FIELD
   for (auto& c : cols) if (!c.dev[0] || !c.dev[1]) return fail(ctx, -9, "arena sizing");
@@ -1379,7 +1385,10 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     dv[s].counters = (int64_t*)ac.take(OPTB_C_COUNT * 8);
     ws[s] = ac.take((size_t)wsb);
     if (!ws[s] || !dv[s].counters) return fail(ctx, -9, "arena sizing");
+    dv[s].root_flags = nullptr;
   }
+  void* sort_ws = sortb ? ac.take((size_t)sortb) : nullptr;
+  if (sortb && !sort_ws) return fail(ctx, -9, "arena sizing");
   if (prm->record_hist && scene->n_mons) {
     CK(cudaMemsetAsync(d_hy, 0, hy, ctx->s_run), "memset hist");
     CK(cudaMemsetAsync(d_hyz, 0, hyz, ctx->s_run), "memset hist");
@@ -1389,7 +1398,7 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     explicit Events(int n) : v(n) { for (auto& e : v) cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
     ~Events() { for (auto& e : v) cudaEventDestroy(e); }
     cudaEvent_t& operator[](int i) { return v[i]; }
-  } ev_h2d(nch), ev_run(nch), ev_d2h(nch);
+  } ev_h2d(nch), ev_run(nch), ev_d2h(nch), ev_sorted(nch);
   unsigned long long tot[OPTB_C_COUNT] = {0};
   int64_t seg_off = 0, hit_off = 0;
   bool chunk_overflow = false;
@@ -1402,6 +1411,14 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     int64_t room[2] = {segcap - seg_off, hitcap - hit_off};
     for (int kind = 0; kind < 2; kind++)
       if (rows[kind] > room[kind]) { rows[kind] = std::max<int64_t>(room[kind], 0); tot[OPTB_C_STATUS] |= kind ? OPTB_ST_HIT_OVERFLOW : OPTB_ST_SEG_OVERFLOW; }
+    if (prm->sorted_rows) {
+      // reference order inside the chunk (chunks follow each other in ray order): sorted on the trace stream, behind
+      // the trace of the next chunk that is already enqueued there; the copy-back stream waits for it
+      int src = optb_sort_rows(ctx, &dv[k & 1], prm->record_segments ? rows[0] : 0, prm->record_hits ? rows[1] : 0, sort_ws, sortb, ctx->s_run);
+      if (src) return src;
+      CK(cudaEventRecord(ev_sorted[k], ctx->s_run), "event");
+      CK(cudaStreamWaitEvent(ctx->s_d2h, ev_sorted[k], 0), "wait");
+    }
     for (auto& c : cols) {
       const int64_t r = rows[c.kind], off = c.kind ? hit_off : seg_off;
       if (r > 0) CK(cudaMemcpyAsync(c.host + (size_t)off * c.elt, c.dev[k & 1], (size_t)r * c.elt, cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H rows");
@@ -1488,7 +1505,8 @@ static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_ra
   const int64_t wsb = needs_serial(scene, rays, prm) ? optb_workspace_bytes(scene, n, 16 * std::max<int64_t>(live, 64))
                                                : (int64_t)ws_layout(n, max_live, split).total;
   const int nfam = std::max(prm->n_families, 1);
-  size_t need = 256 * 64 + (size_t)n * (8 * 13 + 8) + (size_t)segcap * (13 * 8 + 16) + (size_t)hitcap * (10 * 8 + 12) +
+  const int64_t sortb = prm->sorted_rows ? optb_sort_workspace_bytes(std::max(segcap, hitcap)) : 0;
+  size_t need = 256 * 64 + (size_t)sortb + (size_t)n * (8 * 13 + 8) + (size_t)segcap * (13 * 8 + 16) + (size_t)hitcap * (10 * 8 + 12 + 8) +
                 (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 8 +
                 (size_t)std::max(scene->n_caps, 1) * nfam * 4 + 64 * 8 + (size_t)wsb;
   if (ctx->arena_bytes < need) {
@@ -1528,7 +1546,11 @@ static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_ra
   add((void**)&dv.hit_pop, out->hit_pop, 4, hitcap, 1);
   double** hit_d = &dv.hit_px; double* const* hit_h = &out->hit_px;
   for (int f = 0; f < 10; f++) add((void**)&hit_d[f], hit_h[f], 8, hitcap, 1);
+  add((void**)&dv.hit_key, out->hit_key, 8, hitcap, 1);
+  dv.root_flags = nullptr;
   for (auto& c : cols) if (!*c.dev) return fail(ctx, -9, "arena sizing");
+  void* sort_ws = sortb ? ac.take((size_t)sortb) : nullptr;
+  if (sortb && !sort_ws) return fail(ctx, -9, "arena sizing");
   const size_t hy = (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * 8, hyz = hy * OPTB_HIST_BINS;
   dv.hist_y = (int64_t*)ac.take(hy); dv.hist_yz = (int64_t*)ac.take(hyz);
   const size_t capb = (size_t)std::max(scene->n_caps, 1) * nfam * 4;
@@ -1545,6 +1567,8 @@ static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_ra
   if (out->counters) memcpy(out->counters, ctx->h_counters, OPTB_C_COUNT * 8);
   int64_t nseg = std::min<int64_t>((int64_t)ctx->h_counters[OPTB_C_SEGMENTS], segcap);
   int64_t nhit = std::min<int64_t>((int64_t)ctx->h_counters[OPTB_C_HITS], hitcap);
+  if (prm->sorted_rows)
+    if (int src = optb_sort_rows(ctx, &dv, prm->record_segments ? nseg : 0, prm->record_hits ? nhit : 0, sort_ws, sortb, st)) return src;
   for (auto& c : cols) {
     int64_t rows = c.kind == 0 ? nseg : nhit;
     if (rows > 0) CK(cudaMemcpyAsync(c.host, *c.dev, (size_t)rows * c.elt, cudaMemcpyDeviceToHost, st), "D2H results");
@@ -1586,6 +1610,110 @@ extern "C" int optb_measure_fp64_peak(optb_ctx* ctx, double* tflops_out) {
   return 0;
 }
 
+
+// ---- rows into reference order ------------------------------------------------------------------------------------
+namespace {
+__global__ void seg_keys_kernel(const uint32_t* __restrict__ root, const uint32_t* __restrict__ pop, long long n,
+                                unsigned long long* __restrict__ key, uint32_t* __restrict__ idx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    key[i] = ((unsigned long long)root[i] << 32) | pop[i];
+    idx[i] = (uint32_t)i;
+  }
+}
+__global__ void hit_keys_kernel(const unsigned long long* __restrict__ packed, const uint32_t* __restrict__ root,
+                                const int32_t* __restrict__ mon, const uint32_t* __restrict__ pop, long long n,
+                                unsigned long long* __restrict__ key, uint32_t* __restrict__ idx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    key[i] = packed ? packed[i]
+                    : (((unsigned long long)root[i] << 32) | ((unsigned long long)(uint32_t)mon[i] << 24) | pop[i]);
+    idx[i] = (uint32_t)i;
+  }
+}
+template <class T>
+__global__ void gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, long long n, T* __restrict__ dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[idx[i]];
+}
+struct SortLayout { size_t key_a, key_b, idx_a, idx_b, tmp, cub, cub_bytes, total; };
+SortLayout sort_layout(long long n) {
+  SortLayout L{};
+  n = std::max<long long>(n, 1);
+  size_t o = 0;
+  L.key_a = o; o += align_up((size_t)n * 8, 256);
+  L.key_b = o; o += align_up((size_t)n * 8, 256);
+  L.idx_a = o; o += align_up((size_t)n * 4, 256);
+  L.idx_b = o; o += align_up((size_t)n * 4, 256);
+  L.tmp = o; o += align_up((size_t)n * 8, 256);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)std::min<long long>(n, 0x7fffffffll), 0, 64);
+  L.cub = o; L.cub_bytes = align_up(tb + 256, 256); o += L.cub_bytes;
+  L.total = o;
+  return L;
+}
+template <class T>
+int reorder_column(optb_ctx* ctx, T* col, const uint32_t* order, long long n, void* tmp, int grid, cudaStream_t st) {
+  if (!col) return 0;
+  gather_kernel<T><<<grid, 256, 0, st>>>(col, order, n, (T*)tmp);
+  CK(cudaMemcpyAsync(col, tmp, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st), "reorder column");
+  return 0;
+}
+}  // namespace
+
+extern "C" int64_t optb_sort_workspace_bytes(int64_t n_rows) { return n_rows < 0 ? -1 : (int64_t)sort_layout(n_rows).total; }
+
+extern "C" int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_seg, int64_t n_hit, void* workspace,
+                              int64_t workspace_bytes, void* stream_v) {
+  if (!ctx || !res) return -1;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream_v;
+  const long long nmax = std::max<long long>(n_seg, n_hit);
+  if (nmax <= 0) return 0;
+  if (nmax >= 0x7fffffffll) return fail(ctx, -7, "optb_sort_rows: at most 2^31-1 rows");
+  const SortLayout L = sort_layout(nmax);
+  if (!workspace || workspace_bytes < (int64_t)L.total) return fail(ctx, -8, "optb_sort_rows: workspace too small (optb_sort_workspace_bytes)");
+  unsigned char* ws = (unsigned char*)workspace;
+  unsigned long long* key_a = (unsigned long long*)(ws + L.key_a);
+  unsigned long long* key_b = (unsigned long long*)(ws + L.key_b);
+  uint32_t* idx_a = (uint32_t*)(ws + L.idx_a);
+  uint32_t* idx_b = (uint32_t*)(ws + L.idx_b);
+  void* tmp = ws + L.tmp;
+  for (int pass = 0; pass < 2; pass++) {
+    const long long n = pass == 0 ? n_seg : n_hit;
+    if (n <= 1) continue;
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    if (pass == 0) {
+      if (!res->seg_root || !res->seg_pop) return fail(ctx, -7, "optb_sort_rows: seg_root and seg_pop are the segment key");
+      seg_keys_kernel<<<grid, 256, 0, st>>>(res->seg_root, res->seg_pop, n, key_a, idx_a);
+    } else {
+      if (!res->hit_key && !(res->hit_root && res->hit_pop && res->hit_monitor))
+        return fail(ctx, -7, "optb_sort_rows: hit_key, or hit_root + hit_monitor + hit_pop, is the monitor-row key");
+      hit_keys_kernel<<<grid, 256, 0, st>>>((const unsigned long long*)res->hit_key, res->hit_root, res->hit_monitor, res->hit_pop, n, key_a, idx_a);
+    }
+    size_t tb = L.cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, (const unsigned long long*)key_a, key_b, (const uint32_t*)idx_a, idx_b,
+                                       (int)n, 0, 64, st), "radix sort of the row keys");
+    int rc = 0;
+    if (pass == 0) {
+      double* const* f = &res->seg_ox;
+      for (int c = 0; c < 13 && !rc; c++) rc = reorder_column<double>(ctx, f[c], idx_b, n, tmp, grid, st);
+      if (!rc) rc = reorder_column<uint32_t>(ctx, res->seg_flags, idx_b, n, tmp, grid, st);
+      if (!rc) rc = reorder_column<uint32_t>(ctx, res->seg_root, idx_b, n, tmp, grid, st);
+      if (!rc) rc = reorder_column<uint32_t>(ctx, res->seg_pop, idx_b, n, tmp, grid, st);
+      if (!rc) rc = reorder_column<int32_t>(ctx, res->seg_leaf, idx_b, n, tmp, grid, st);
+    } else {
+      double* const* f = &res->hit_px;
+      for (int c = 0; c < 10 && !rc; c++) rc = reorder_column<double>(ctx, f[c], idx_b, n, tmp, grid, st);
+      if (!rc) rc = reorder_column<int32_t>(ctx, res->hit_monitor, idx_b, n, tmp, grid, st);
+      if (!rc) rc = reorder_column<uint32_t>(ctx, res->hit_root, idx_b, n, tmp, grid, st);
+      if (!rc) rc = reorder_column<uint32_t>(ctx, res->hit_pop, idx_b, n, tmp, grid, st);
+      if (!rc) rc = reorder_column<unsigned long long>(ctx, (unsigned long long*)res->hit_key, idx_b, n, tmp, grid, st);
+    }
+    if (rc) return rc;
+  }
+  CK(cudaGetLastError(), "optb_sort_rows");
+  return 0;
+}
 
 // ---- multi-GPU monitor merge over NCCL (loaded at run time: no link-time dependency) ------------------------------
 namespace {

@@ -45,8 +45,9 @@ def _closure_map(fn):
 
 
 class _Materials:
-    def __init__(self):
+    def __init__(self, wavelengths_m=None, aux=None):
         self.kind, self.f, self._index = [], [], {}
+        self.wavelengths_m, self.aux = wavelengths_m, aux
 
     def add(self, m) -> int:
         key, kind, row = self._describe(m)
@@ -57,8 +58,23 @@ class _Materials:
         self.f.append(row)
         return self._index[key]
 
-    @staticmethod
-    def _describe(m):
+    def _lut(self, m):
+        """Material(name, n=<any callable>) (material.py:4-21): the device cannot run Python, so the host evaluates
+        the callable once per DISTINCT wavelength of the batch (metres = ray.wavelength * ray.unit, the product the
+        reference's RefractiveIndex descriptor forms, material.py:54-85) and ships (wavelength, n) pairs sorted by
+        wavelength. Same callable, same argument, same float: the index a ray sees is the
+        reference's, bit for bit."""
+        if self.wavelengths_m is None:
+            raise FlattenError(f"material {m!r} is an arbitrary n(wavelength) callable: pass the batch's wavelengths "
+                               "(FlatScene(..., wavelengths_m=...); OpticalTable.ray_tracing / trace_bundle do)")
+        row = [0.0] * A.MF_STRIDE
+        ws = sorted({float(w) for w in self.wavelengths_m})
+        row[0], row[1] = float(len(self.aux)), float(len(ws))
+        for w in ws:
+            self.aux.extend([w, float(m.n(w))])
+        return ("lut", id(m)), A.MAT_LUT, row
+
+    def _describe(self, m):
         row = [0.0] * A.MF_STRIDE
         if isinstance(m, (int, float, np.integer, np.floating)):
             row[0] = float(m)
@@ -76,7 +92,7 @@ class _Materials:
             if set(cm) == {"n"} and isinstance(cm["n"], (int, float, np.integer, np.floating)):
                 nc = cm["n"]
         if nc is None:
-            raise FlattenError(f"material {m!r}: arbitrary n(wavelength) callables are not supported on the device")
+            return self._lut(m)
         row[0] = float(nc)
         return ("c", row[0]), A.MAT_CONST, row
 
@@ -119,9 +135,11 @@ _BVH_PLANS = {}  # (fanout, n, box bytes) -> hierarchy plan, see FlatScene._wrap
 class FlatScene:
     """Numpy tables + bookkeeping for one OpticalTable."""
 
-    def __init__(self, components, monitors=()):
+    def __init__(self, components, monitors=(), wavelengths_m=None):
+        """`wavelengths_m`: the distinct wavelengths (metres) of the rays that will be traced; only needed when a
+        material of the scene is an arbitrary Python callable (per-wavelength table, see _Materials._lut)."""
         self._ni, self._nf, self._aux = [], [], []
-        self._mats = _Materials()
+        self._mats = _Materials(wavelengths_m, self._aux)
         self.leaves = []       # leaf index -> component object
         self.capslots = []     # cap slot -> component object
         self.max_children = 0  # most rays one interaction can emit (<=1: no splitting anywhere)
@@ -554,6 +572,12 @@ def pack_rays(rays):
         raise FlattenError("rays with different .unit in one batch are not supported")
     out["flags"], out["family"] = flags, family
     return out, fam_ids, (units.pop() if units else 1e-2)
+
+
+def batch_wavelengths_m(wavelength_column, unit):
+    """Distinct values of ray.wavelength * ray.unit of a batch (what Material.n is called with, optical_component.py:627-628)."""
+    w = np.unique(np.asarray(wavelength_column, dtype=np.float64).reshape(-1))
+    return (w * float(unit)).tolist()
 
 
 def rays_struct(arrs, n=None) -> A.Rays:

@@ -19,7 +19,7 @@ import numpy as np
 from . import _abi as A
 from .assemblies import ComponentGroup
 from .elements import OpticalComponent
-from .flatten import FlatScene, pack_rays, trace_cap
+from .flatten import FlatScene, batch_wavelengths_m, pack_rays, trace_cap
 from .monitors import Monitor
 from .rays import Ray
 
@@ -97,8 +97,8 @@ def trace_table(table, rays, perfomance_limit=None, engine=None):
     from .backend import Engine
 
     engine = engine or Engine.get()
-    flat = FlatScene(table.components, table.monitors)
     arrs, fam_ids, unit = pack_rays(rays)
+    flat = FlatScene(table.components, table.monitors, wavelengths_m=batch_wavelengths_m(arrs["wavelength"], unit))
     caps = None
     if flat.n_capslots:
         caps = np.zeros((flat.n_capslots, len(fam_ids)), np.int32)
@@ -156,8 +156,8 @@ def single_pop(component, ray, engine=None):
     if not ray.alive:
         return None, None
     engine = engine or Engine.get()
-    flat = FlatScene([component], [])
     arrs, fam_ids, unit = pack_rays([ray])
+    flat = FlatScene([component], [], wavelengths_m=batch_wavelengths_m(arrs["wavelength"], unit))
     caps = None
     if flat.n_capslots:
         caps = np.array([[c._interact_count.get(ray._id, 0)] for c in flat.capslots], np.int32)
@@ -287,12 +287,12 @@ class OpticalTable:
         mine = [m for m in self.monitors if m is mon0 or m is mon1]
         if type(self).ray_tracing is not OpticalTable.ray_tracing or len(mine) != len(self.monitors) or len(mine) != 2:
             return None
-        flat = FlatScene(self.components, [mon0, mon1])
-        if flat.n_capslots:
-            return None
         n = len(work)
         batch = work + [r.copy()._Translate(shift) for r in work]
         arrs, fam_ids, unit = pack_rays(batch)
+        flat = FlatScene(self.components, [mon0, mon1], wavelengths_m=batch_wavelengths_m(arrs["wavelength"], unit))
+        if flat.n_capslots:
+            return None
         engine = Engine.get()
         scene = engine.upload(flat)
         try:

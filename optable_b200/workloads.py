@@ -18,6 +18,13 @@ class Scene:
     def __init__(self, components, rays, monitors=(), limit=None):
         self.components, self.rays, self.monitors, self.limit = list(components), list(rays), list(monitors), limit
 
+    def flat(self):
+        """Device tables of the scene (the rays' wavelengths ride along for per-wavelength material tables)."""
+        from .flatten import FlatScene
+
+        wl = sorted({(0.0 if r.wavelength is None else float(r.wavelength)) * float(r.unit) for r in self.rays})
+        return FlatScene(self.components, self.monitors, wavelengths_m=wl or None)
+
 
 def cavity(ns, dt1=0.02, dt2=0.02, gaussian=False, n_rays=1, limit=None):
     """examples/cavity_4mir.py:17-40 (misaligned: escapes after 21 bounces; aligned: runs to the cap)."""

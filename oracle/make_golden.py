@@ -27,7 +27,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 def make(name):
     ref = RH.load_reference()
     sc = scenes.REGISTRY[name](ref)
-    flat = FlatScene(sc.components, sc.monitors)
+    flat = sc.flat()
     arrs, fam_ids, unit = pack_rays(sc.rays)
     r = RH.run_reference(sc)
     leaves = r.pop("_leaves")

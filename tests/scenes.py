@@ -359,6 +359,23 @@ def fuzz(ns, seed, n_rays=24, caps=False, extended=False):
     return Scene(comps, rays, mons, limit={"max_trace_num": 60})
 
 
+def callable_material(ns):
+    """a19: `Material(name, n=<arbitrary Python callable>)` (material.py:4-21) on both sides of a tilted slab and in a
+    plano-convex lens, three wavelengths sharing ray ids (multiplex_rays_in_wavelength): a Cauchy law written as a
+    plain lambda, which the device can only get as a per-wavelength table evaluated by the host."""
+    cauchy = ns.Material("Cauchy", n=lambda wl_m: 1.5046 + 4.2e-15 / wl_m ** 2)
+    flint = ns.Material("tab", n=lambda wl_m: float(np.interp(wl_m, [3e-7, 6e-7, 12e-7], [1.74, 1.68, 1.65])))
+    slab = ns.GlassSlab([4, 0, 0], width=4, height=4, thickness=0.7, n1=ns.Vacuum(), n2=cauchy, reflectivity=0.05).RotZ(0.3)
+    face = ns.CircleRefractive([8, 0, 0], radius=2.0, n1=1.0, n2=flint)
+    back = ns.SphereRefractive([8.9 - 6.0, 0, 0], radius=6.0, height=0.4, n1=1.0, n2=flint)
+    mon = ns.Monitor([14, 0, 0], 8, 8)
+    rng = np.random.default_rng(SEED + 9)
+    r0 = [ns.Ray([0, y, z], [1, 0.02 * rng.standard_normal(), 0.02 * rng.standard_normal()], wavelength=780e-7, w0=50e-4)
+          for y, z in rng.uniform(-0.8, 0.8, (5, 2))]
+    rays = ns.multiplex_rays_in_wavelength(r0, [780e-7, 532e-7, 405e-7])
+    return Scene([slab, face, back], rays, [mon], limit={"max_trace_num": 60})
+
+
 REGISTRY = {
     "gaussian_beam": gaussian_beam,
     "glass_slab": glass_slab,
@@ -378,6 +395,7 @@ REGISTRY = {
     "extras": extras,
     "ripa": lambda ns: ripa(ns, n_rays=3, limit=150),
     "ripa2_simplified": ripa2_simplified,
+    "callable_material": callable_material,
 }
 # a dozen random scenes are ordinary fixtures too (reference-generated goldens); the fuzz tests add hundreds more
 for _seed in range(12):

@@ -27,7 +27,7 @@ def _q_rtol(name):
     import optable_b200 as ob
 
     sc = scenes.REGISTRY[name](ob)
-    return parity.q_rtol_for(FlatScene(sc.components, sc.monitors))
+    return parity.q_rtol_for(sc.flat())
 
 
 @pytest.mark.parametrize("name", sorted(scenes.REGISTRY))

@@ -59,7 +59,7 @@ def _fuzz_block(engine, seeds, **fuzz_kw):
     pops = flagged = rays = restarted = 0
     for seed in seeds:
         sc = scenes.fuzz(ob, seed, n_rays=64, **fuzz_kw)
-        flat = FlatScene(sc.components, sc.monitors)
+        flat = sc.flat()
         arrs, fam_ids, unit = pack_rays(sc.rays)
         params = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
         raw = O.trace(flat, arrs, **params)
@@ -119,7 +119,7 @@ def test_fuzz_scenes_with_binding_interact_caps(engine):
     reached = flagged = 0
     for seed in range(300, 340):
         sc = scenes.fuzz(ob, seed, caps=True)
-        flat = FlatScene(sc.components, sc.monitors)
+        flat = sc.flat()
         arrs, fam_ids, unit = pack_rays(sc.rays)
         params = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
         raw = O.trace(flat, arrs, **params)

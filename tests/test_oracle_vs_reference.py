@@ -13,7 +13,7 @@ pytestmark = pytest.mark.skipif(not RH.reference_available(), reason="/root/refe
 def test_oracle_vs_live_reference(name, capsys):
     ref = RH.load_reference()
     sc = scenes.REGISTRY[name](ref)
-    flat = FlatScene(sc.components, sc.monitors)
+    flat = sc.flat()
     arrs, fam_ids, unit = pack_rays(sc.rays)
     want = RH.run_reference(sc)
     got = O.trace(flat, arrs, max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
@@ -32,7 +32,7 @@ def test_fuzz_scenes_oracle_equals_reference(block):
     flagged = rays = 0
     for seed in range(100 + 10 * block, 110 + 10 * block):
         sc = scenes.fuzz(ref, seed)
-        flat = FlatScene(sc.components, sc.monitors)
+        flat = sc.flat()
         arrs, fam_ids, unit = pack_rays(sc.rays)
         want = RH.run_reference(sc)
         got = O.trace(flat, arrs, max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
@@ -54,7 +54,7 @@ def test_fuzz_scenes_with_binding_interact_caps():
     reached = 0
     for seed in range(300, 316):
         sc = scenes.fuzz(ref, seed, caps=True)
-        flat = FlatScene(sc.components, sc.monitors)
+        flat = sc.flat()
         arrs, fam_ids, unit = pack_rays(sc.rays)
         want = RH.run_reference(sc)
         want.pop("_leaves", None)
@@ -77,7 +77,7 @@ def test_fuzz_scenes_whole_zoo(block):
     for seed in range(800 + 12 * block, 812 + 12 * block):
         caps = seed % 3 == 0
         sc = scenes.fuzz(ref, seed, caps=caps, extended=True)
-        flat = FlatScene(sc.components, sc.monitors)
+        flat = sc.flat()
         arrs, fam_ids, unit = pack_rays(sc.rays)
         want = RH.run_reference(sc)
         want.pop("_leaves", None)

@@ -14,7 +14,7 @@ from tests import golden_io, scenes
 def test_flattened_tables_match_reference_classes(name):
     want_flat, want_rays, want_params, _ = golden_io.load(name)
     sc = scenes.REGISTRY[name](ob)
-    flat = FlatScene(sc.components, sc.monitors)
+    flat = sc.flat()
     # Leaves (and their order) must agree exactly; the synthetic box hierarchy above them may be cut at
     # different, equally valid places when box coordinates differ in the last bits, so `skip` and the wrapper
     # rows are not compared (the wrappers are exact by construction, see FlatScene._wrap_runs).
@@ -137,3 +137,23 @@ def test_random_constructions_match_reference_classes(block):
                 np.testing.assert_allclose(rb[k], ra[k], rtol=1e-13, atol=1e-15)
             else:
                 np.testing.assert_array_equal(rb[k], ra[k])
+
+
+def test_callable_material_becomes_a_per_wavelength_table():
+    """a19: Material(n=<callable>) -> OPTB_MAT_LUT rows evaluated by the host at the batch's distinct wavelengths
+    (metres); without the wavelengths the flattener refuses (there is no CPU fallback to hide behind)."""
+    from optable_b200 import _abi as A
+    from optable_b200.flatten import FlattenError
+
+    sc = scenes.callable_material(ob)
+    with pytest.raises(FlattenError):
+        FlatScene(sc.components, sc.monitors)
+    flat = sc.flat()
+    lut = np.nonzero(flat.mat_kind == A.MAT_LUT)[0]
+    assert len(lut) == 2
+    wl = sorted({r.wavelength * r.unit for r in sc.rays})
+    for m in lut:
+        off, cnt = int(flat.mat_f[m, 0]), int(flat.mat_f[m, 1])
+        tab = flat.aux[off:off + 2 * cnt].reshape(-1, 2)
+        np.testing.assert_array_equal(tab[:, 0], wl)
+        assert np.all(tab[:, 1] > 1.4) and np.all(np.diff(tab[:, 1]) < 0)   # normal dispersion of both laws

@@ -12,7 +12,7 @@ from tests import scenes
 
 seed = int(sys.argv[1]); n_rays = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 sc = scenes.fuzz(ob, seed, n_rays=n_rays)
-flat = FlatScene(sc.components, sc.monitors)
+flat = sc.flat()
 arrs, fam, unit = pack_rays(sc.rays)
 prm = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam))
 want = O.trace(flat, arrs, **prm)

@@ -24,7 +24,7 @@ kinds = collections.Counter()
 t0 = time.time()
 for seed in range(first, first + count):
     sc = scenes.fuzz(ob, seed, n_rays=n_rays, caps=CAPS, extended=EXTENDED)
-    flat = FlatScene(sc.components, sc.monitors)
+    flat = sc.flat()
     arrs, fam, unit = pack_rays(sc.rays)
     prm = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam))
     raw = O.trace(flat, arrs, **prm)
