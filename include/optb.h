@@ -353,6 +353,35 @@ int64_t optb_sort_workspace_bytes(int64_t n_rows);
 int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_seg, int64_t n_hit,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- monitor analytics on the device (monitor.py:78-253) ----------------------------------------
+ * One fused pass over monitor rows that are still in HBM: for the rows [first, first + n) of `rows` that belong to
+ * `monitor` (-1: every row of the range) it evaluates what the reference's Monitor accessors derive per row --
+ *   y = P_local . tangent_Y, z = P_local . tangent_Z   (get_yList / get_zList :78-100; LOCAL point, LAB tangent: the
+ *                                                        reference's own convention, kept)
+ *   tY = d . tangent_Y, tZ = d . tangent_Z             (get_tYList / tZList :137-157)
+ *   waist distance = +-Re(q + t), minus when d . normal > 0   (get_waist_distance :202-216)
+ * -- writes them to the optional per-row columns (NaN for rows of other monitors) and accumulates, in the same pass,
+ * the row count, sum of intensities (sum_intensity / avg_intensity :236-242), first and second moments and extrema of
+ * y and z, the sum of the waist distances and the 30-bin np.histogram of y over +-width/2 (_get_hist_y :195-200,
+ * from which std_histy :244-249 follows). No row leaves the device.                                              */
+typedef struct optb_monitor_frame {
+  double tangent_y[3], tangent_z[3], normal[3]; /* Monitor.tangent_Y / tangent_Z / normal (lab frame) */
+  double half_width, half_height;
+} optb_monitor_frame;
+enum {
+  OPTB_MS_COUNT = 0, OPTB_MS_SUM_I = 1, OPTB_MS_SUM_Y = 2, OPTB_MS_SUM_YY = 3, OPTB_MS_SUM_Z = 4, OPTB_MS_SUM_ZZ = 5,
+  OPTB_MS_SUM_WD = 6, OPTB_MS_MIN_Y = 7, OPTB_MS_MAX_Y = 8, OPTB_MS_MIN_Z = 9, OPTB_MS_MAX_Z = 10,
+  OPTB_MS_SUM_TY = 11, OPTB_MS_SUM_TYTY = 12,
+  OPTB_MS_HIST = 16, /* 30 counts */
+  OPTB_MS_STRIDE = 48
+};
+/* rows: DEVICE pointers (hit_px/py/pz, hit_intensity, hit_t required; hit_dx..dz for tY/tZ/waist sign, hit_q_re for the
+ * waist distance; hit_monitor or hit_key when monitor >= 0). stats: device double[OPTB_MS_STRIDE], overwritten.
+ * y, z, ty, tz, waist: device double[n] or NULL.                                                                  */
+int optb_monitor_stats(optb_ctx* ctx, const optb_result* rows, int64_t first, int64_t n, int monitor,
+                       const optb_monitor_frame* frame, double* stats, double* y, double* z, double* ty, double* tz,
+                       double* waist, void* stream);
+
 /* ---- multi-GPU monitor merge -----------------------------------------------------------------------
  * The path shards without a data-path collective: every rank (one process per GPU, one ctx each) traces its own block
  * of the initial rays against its own copy of the scene. The only exchange is the merge of the monitors at the end,

@@ -83,6 +83,16 @@ EXPORTED_SYMBOLS = (
     "optb_abi_version", "optb_ctx_create", "optb_ctx_destroy", "optb_last_error",
     "optb_scene_upload", "optb_scene_destroy", "optb_workspace_bytes", "optb_trace",
     "optb_trace_host", "optb_measure_fp64_peak",
-    "optb_sort_workspace_bytes", "optb_sort_rows",
+    "optb_sort_workspace_bytes", "optb_sort_rows", "optb_monitor_stats",
     "optb_comm_unique_id", "optb_comm_init", "optb_monitor_merge", "optb_comm_destroy",
 )
+
+
+class MonitorFrame(C.Structure):
+    _fields_ = [("tangent_y", C.c_double * 3), ("tangent_z", C.c_double * 3), ("normal", C.c_double * 3),
+                ("half_width", C.c_double), ("half_height", C.c_double)]
+
+
+(MS_COUNT, MS_SUM_I, MS_SUM_Y, MS_SUM_YY, MS_SUM_Z, MS_SUM_ZZ, MS_SUM_WD, MS_MIN_Y, MS_MAX_Y, MS_MIN_Z, MS_MAX_Z,
+ MS_SUM_TY, MS_SUM_TYTY) = range(13)
+MS_HIST, MS_STRIDE = 16, 48

@@ -817,6 +817,9 @@ static int fail(optb_ctx* ctx, int code, const char* what, cudaError_t e = cudaS
 extern "C" int optb_abi_version(void) { return OPTB_ABI_VERSION; }
 extern "C" int optb_comm_destroy(optb_ctx* ctx);
 extern "C" int64_t optb_sort_workspace_bytes(int64_t n_rows);
+static int sort_rows_dev(optb_ctx* ctx, const optb_result* res, const optb_result* dst, int64_t n_seg, int64_t n_hit,
+                         const unsigned long long* d_counters, void* workspace, int64_t workspace_bytes, cudaStream_t st,
+                         int end_bit);
 extern "C" int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_seg, int64_t n_hit, void* workspace,
                               int64_t workspace_bytes, void* stream_v);
 
@@ -1330,7 +1333,7 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     ctx->h_chunk_n = nch;
   }
   const int64_t sortb = prm->sorted_rows ? optb_sort_workspace_bytes(std::max(cseg, chit)) : 0;
-  size_t need = 256 * 128 + (size_t)n * (8 * 13 + 8) + 2 * ((size_t)cseg * (13 * 8 + 16) + (size_t)chit * (10 * 8 + 12 + 8)) +
+  size_t need = 256 * 128 + (size_t)n * (8 * 13 + 8) + (prm->sorted_rows ? 4 : 2) * ((size_t)cseg * (13 * 8 + 16) + (size_t)chit * (10 * 8 + 12 + 8) + 40 * 256) +
                 (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 8 + 2 * (64 * 8 + (size_t)wsb) +
                 (size_t)sortb + 4096;
   if (ctx->arena_bytes < need) {
@@ -1353,14 +1356,21 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
   }
   if (rays->flags) dr.flags = (const uint32_t*)ac.take((size_t)n * 4);
   if (rays->family) dr.family = (const int32_t*)ac.take((size_t)n * 4);
-  struct Col { void* dev[2]; unsigned char* host; size_t elt; int kind; };
+  // dev: the two result sets the traces of even / odd chunks append to; srt (sorted_rows): the same rows in reference
+  // order, gathered there right behind the trace, so that the copy back never waits for a later chunk's trace
+  struct Col { void* dev[2]; void* srt[2]; unsigned char* host; size_t elt; int kind; };
   std::vector<Col> cols;
-  optb_result dv[2] = {*out, *out};
+  optb_result dv[2] = {*out, *out}, sv[2] = {*out, *out};
+  const bool sorted = prm->sorted_rows != 0;
   auto add = [&](size_t field_off, void* host_ptr, size_t elt, int64_t capn, int kind) {
-    for (int s = 0; s < 2; s++) *(void**)((unsigned char*)&dv[s] + field_off) = nullptr;
+    for (int s = 0; s < 2; s++) *(void**)((unsigned char*)&dv[s] + field_off) = *(void**)((unsigned char*)&sv[s] + field_off) = nullptr;
     if (!host_ptr || capn == 0) return;
-    Col c{{ac.take((size_t)capn * elt), ac.take((size_t)capn * elt)}, (unsigned char*)host_ptr, elt, kind};
-    for (int s = 0; s < 2; s++) *(void**)((unsigned char*)&dv[s] + field_off) = c.dev[s];
+    Col c{{ac.take((size_t)capn * elt), ac.take((size_t)capn * elt)}, {nullptr, nullptr}, (unsigned char*)host_ptr, elt, kind};
+    if (sorted) { c.srt[0] = ac.take((size_t)capn * elt); c.srt[1] = ac.take((size_t)capn * elt); }
+    for (int s = 0; s < 2; s++) {
+      *(void**)((unsigned char*)&dv[s] + field_off) = c.dev[s];
+      *(void**)((unsigned char*)&sv[s] + field_off) = c.srt[s];
+    }
     cols.push_back(c);
   };
 #define OPTB_FIELD(name) offsetof(optb_result, name), (void*)out->name
@@ -1375,7 +1385,9 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     add(OPTB_FIELD(hit_key), 8, chit, 1);
   }
 #undef OPTB_FIELD
-  for (auto& c : cols) if (!c.dev[0] || !c.dev[1]) return fail(ctx, -9, "arena sizing");
+  for (auto& c : cols) if (!c.dev[0] || !c.dev[1] || (sorted && (!c.srt[0] || !c.srt[1]))) return fail(ctx, -9, "arena sizing");
+  int end_bit = 33;  // keys are root << 32 | ...: sort only the bits a root index of this batch can occupy
+  while (end_bit < 64 && (1ull << (end_bit - 32)) <= (unsigned long long)n) end_bit++;
   const size_t hy = (size_t)std::max(scene->n_mons, 1) * OPTB_HIST_BINS * 8, hyz = hy * OPTB_HIST_BINS;
   int64_t* d_hy = (int64_t*)ac.take(hy); int64_t* d_hyz = (int64_t*)ac.take(hyz);
   void* ws[2];
@@ -1398,7 +1410,7 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     explicit Events(int n) : v(n) { for (auto& e : v) cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
     ~Events() { for (auto& e : v) cudaEventDestroy(e); }
     cudaEvent_t& operator[](int i) { return v[i]; }
-  } ev_h2d(nch), ev_run(nch), ev_d2h(nch), ev_sorted(nch);
+  } ev_h2d(nch), ev_run(nch), ev_d2h(nch);
   unsigned long long tot[OPTB_C_COUNT] = {0};
   int64_t seg_off = 0, hit_off = 0;
   bool chunk_overflow = false;
@@ -1411,17 +1423,9 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     int64_t room[2] = {segcap - seg_off, hitcap - hit_off};
     for (int kind = 0; kind < 2; kind++)
       if (rows[kind] > room[kind]) { rows[kind] = std::max<int64_t>(room[kind], 0); tot[OPTB_C_STATUS] |= kind ? OPTB_ST_HIT_OVERFLOW : OPTB_ST_SEG_OVERFLOW; }
-    if (prm->sorted_rows) {
-      // reference order inside the chunk (chunks follow each other in ray order): sorted on the trace stream, behind
-      // the trace of the next chunk that is already enqueued there; the copy-back stream waits for it
-      int src = optb_sort_rows(ctx, &dv[k & 1], prm->record_segments ? rows[0] : 0, prm->record_hits ? rows[1] : 0, sort_ws, sortb, ctx->s_run);
-      if (src) return src;
-      CK(cudaEventRecord(ev_sorted[k], ctx->s_run), "event");
-      CK(cudaStreamWaitEvent(ctx->s_d2h, ev_sorted[k], 0), "wait");
-    }
     for (auto& c : cols) {
       const int64_t r = rows[c.kind], off = c.kind ? hit_off : seg_off;
-      if (r > 0) CK(cudaMemcpyAsync(c.host + (size_t)off * c.elt, c.dev[k & 1], (size_t)r * c.elt, cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H rows");
+      if (r > 0) CK(cudaMemcpyAsync(c.host + (size_t)off * c.elt, sorted ? c.srt[k & 1] : c.dev[k & 1], (size_t)r * c.elt, cudaMemcpyDeviceToHost, ctx->s_d2h), "D2H rows");
     }
     CK(cudaEventRecord(ev_d2h[k], ctx->s_d2h), "event");
     if (prm->record_segments) seg_off += rows[0];
@@ -1441,7 +1445,7 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     if (rays->family) CK(cudaMemcpyAsync((void*)(dr.family + lo), rays->family + lo, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->s_h2d), "H2D family");
     CK(cudaEventRecord(ev_h2d[c], ctx->s_h2d), "event");
     CK(cudaStreamWaitEvent(ctx->s_run, ev_h2d[c], 0), "wait");
-    if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_run, ev_d2h[c - 2], 0), "wait");  // the result set is free again
+    if (c >= 2 && !sorted) CK(cudaStreamWaitEvent(ctx->s_run, ev_d2h[c - 2], 0), "wait");  // the result set is free again
     optb_rays cr = dr;
     cr.n = m;
     const double** cf = &cr.ox;
@@ -1450,6 +1454,15 @@ static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const op
     if (cr.family) cr.family += lo;
     rc = trace_impl(ctx, scene, &cr, prm, &dv[c & 1], ws[c & 1], wsb, ctx->s_run, (uint32_t)lo, false);
     if (rc) break;
+    if (sorted) {
+      // reference order inside the chunk (chunks follow each other in ray order): keys + radix sort + one gather of
+      // all columns into the sorted set, on the trace stream right behind the trace. The row counts stay on the
+      // device (rows beyond them sort to the end), so nothing here waits for the host.
+      if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_run, ev_d2h[c - 2], 0), "wait");  // the sorted set is free again
+      rc = sort_rows_dev(ctx, &dv[c & 1], &sv[c & 1], prm->record_segments ? cseg : 0, prm->record_hits ? chit : 0,
+                         (const unsigned long long*)dv[c & 1].counters, sort_ws, sortb, ctx->s_run, end_bit);
+      if (rc) break;
+    }
     CK(cudaMemcpyAsync(ctx->h_chunk + (size_t)c * OPTB_C_COUNT, dv[c & 1].counters, OPTB_C_COUNT * 8, cudaMemcpyDeviceToHost, ctx->s_run), "D2H counters");
     CK(cudaEventRecord(ev_run[c], ctx->s_run), "event");
     if (c >= 1) rc = drain(c - 1);
@@ -1613,20 +1626,38 @@ extern "C" int optb_measure_fp64_peak(optb_ctx* ctx, double* tflops_out) {
 
 // ---- rows into reference order ------------------------------------------------------------------------------------
 namespace {
+// `d_count` (optional): the number of valid rows lives on the device (a counter of the trace that just ran on the same
+// stream); rows beyond it get the largest key and sort to the end, so the host need not know the count to enqueue the sort
 __global__ void seg_keys_kernel(const uint32_t* __restrict__ root, const uint32_t* __restrict__ pop, long long n,
+                                const unsigned long long* __restrict__ d_count,
                                 unsigned long long* __restrict__ key, uint32_t* __restrict__ idx) {
+  const long long valid = d_count ? (long long)min(*d_count, (unsigned long long)n) : n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    key[i] = ((unsigned long long)root[i] << 32) | pop[i];
+    key[i] = i < valid ? (((unsigned long long)root[i] << 32) | pop[i]) : ~0ull;
     idx[i] = (uint32_t)i;
   }
 }
 __global__ void hit_keys_kernel(const unsigned long long* __restrict__ packed, const uint32_t* __restrict__ root,
                                 const int32_t* __restrict__ mon, const uint32_t* __restrict__ pop, long long n,
+                                const unsigned long long* __restrict__ d_count,
                                 unsigned long long* __restrict__ key, uint32_t* __restrict__ idx) {
+  const long long valid = d_count ? (long long)min(*d_count, (unsigned long long)n) : n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    key[i] = packed ? packed[i]
-                    : (((unsigned long long)root[i] << 32) | ((unsigned long long)(uint32_t)mon[i] << 24) | pop[i]);
+    key[i] = i >= valid ? ~0ull
+             : packed   ? packed[i]
+                        : (((unsigned long long)root[i] << 32) | ((unsigned long long)(uint32_t)mon[i] << 24) | pop[i]);
     idx[i] = (uint32_t)i;
+  }
+}
+// all columns of a row set in one pass: dst[c][i] = src[c][order[i]]
+struct GatherCols { const void* src[20]; void* dst[20]; int elt[20]; int ncol; };
+__global__ void __launch_bounds__(256) gather_rows_kernel(const GatherCols g, const uint32_t* __restrict__ order, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t j = order[i];
+    for (int c = 0; c < g.ncol; c++) {
+      if (g.elt[c] == 8) ((unsigned long long*)g.dst[c])[i] = ((const unsigned long long*)g.src[c])[j];
+      else ((uint32_t*)g.dst[c])[i] = ((const uint32_t*)g.src[c])[j];
+    }
   }
 }
 template <class T>
@@ -1662,11 +1693,12 @@ int reorder_column(optb_ctx* ctx, T* col, const uint32_t* order, long long n, vo
 
 extern "C" int64_t optb_sort_workspace_bytes(int64_t n_rows) { return n_rows < 0 ? -1 : (int64_t)sort_layout(n_rows).total; }
 
-extern "C" int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_seg, int64_t n_hit, void* workspace,
-                              int64_t workspace_bytes, void* stream_v) {
-  if (!ctx || !res) return -1;
-  cudaSetDevice(ctx->device);
-  cudaStream_t st = (cudaStream_t)stream_v;
+// Sort the first n_seg / n_hit rows of `src` by their keys. dst == nullptr: in place (column by column through a
+// scratch column); else every present column of src is gathered into the same column of dst in one pass.
+// d_counters (optional): device counters of the trace that produced the rows; then n_seg / n_hit are capacities.
+static int sort_rows_dev(optb_ctx* ctx, const optb_result* res, const optb_result* dst, int64_t n_seg, int64_t n_hit,
+                         const unsigned long long* d_counters, void* workspace, int64_t workspace_bytes, cudaStream_t st,
+                         int end_bit) {
   const long long nmax = std::max<long long>(n_seg, n_hit);
   if (nmax <= 0) return 0;
   if (nmax >= 0x7fffffffll) return fail(ctx, -7, "optb_sort_rows: at most 2^31-1 rows");
@@ -1680,19 +1712,39 @@ extern "C" int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_s
   void* tmp = ws + L.tmp;
   for (int pass = 0; pass < 2; pass++) {
     const long long n = pass == 0 ? n_seg : n_hit;
-    if (n <= 1) continue;
+    if (n <= 1 && !d_counters) continue;
+    if (n <= 0) continue;
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
     if (pass == 0) {
       if (!res->seg_root || !res->seg_pop) return fail(ctx, -7, "optb_sort_rows: seg_root and seg_pop are the segment key");
-      seg_keys_kernel<<<grid, 256, 0, st>>>(res->seg_root, res->seg_pop, n, key_a, idx_a);
+      seg_keys_kernel<<<grid, 256, 0, st>>>(res->seg_root, res->seg_pop, n, d_counters ? d_counters + OPTB_C_SEGMENTS : nullptr, key_a, idx_a);
     } else {
       if (!res->hit_key && !(res->hit_root && res->hit_pop && res->hit_monitor))
         return fail(ctx, -7, "optb_sort_rows: hit_key, or hit_root + hit_monitor + hit_pop, is the monitor-row key");
-      hit_keys_kernel<<<grid, 256, 0, st>>>((const unsigned long long*)res->hit_key, res->hit_root, res->hit_monitor, res->hit_pop, n, key_a, idx_a);
+      hit_keys_kernel<<<grid, 256, 0, st>>>((const unsigned long long*)res->hit_key, res->hit_root, res->hit_monitor, res->hit_pop, n,
+                                            d_counters ? d_counters + OPTB_C_HITS : nullptr, key_a, idx_a);
     }
     size_t tb = L.cub_bytes;
     CK(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, (const unsigned long long*)key_a, key_b, (const uint32_t*)idx_a, idx_b,
-                                       (int)n, 0, 64, st), "radix sort of the row keys");
+                                       (int)n, 0, end_bit, st), "radix sort of the row keys");
+    if (dst) {
+      GatherCols g;
+      g.ncol = 0;
+      auto col = [&](const void* sp, void* dp, int elt) { if (sp && dp) { g.src[g.ncol] = sp; g.dst[g.ncol] = dp; g.elt[g.ncol] = elt; g.ncol++; } };
+      if (pass == 0) {
+        double* const* f = &res->seg_ox; double* const* fd = &dst->seg_ox;
+        for (int c = 0; c < 13; c++) col(f[c], fd[c], 8);
+        col(res->seg_flags, dst->seg_flags, 4); col(res->seg_root, dst->seg_root, 4);
+        col(res->seg_pop, dst->seg_pop, 4); col(res->seg_leaf, dst->seg_leaf, 4);
+      } else {
+        double* const* f = &res->hit_px; double* const* fd = &dst->hit_px;
+        for (int c = 0; c < 10; c++) col(f[c], fd[c], 8);
+        col(res->hit_monitor, dst->hit_monitor, 4); col(res->hit_root, dst->hit_root, 4);
+        col(res->hit_pop, dst->hit_pop, 4); col(res->hit_key, dst->hit_key, 8);
+      }
+      if (g.ncol) gather_rows_kernel<<<grid, 256, 0, st>>>(g, idx_b, n);
+      continue;
+    }
     int rc = 0;
     if (pass == 0) {
       double* const* f = &res->seg_ox;
@@ -1712,6 +1764,142 @@ extern "C" int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_s
     if (rc) return rc;
   }
   CK(cudaGetLastError(), "optb_sort_rows");
+  return 0;
+}
+
+extern "C" int optb_sort_rows(optb_ctx* ctx, const optb_result* res, int64_t n_seg, int64_t n_hit, void* workspace,
+                              int64_t workspace_bytes, void* stream_v) {
+  if (!ctx || !res) return -1;
+  cudaSetDevice(ctx->device);
+  return sort_rows_dev(ctx, res, nullptr, n_seg, n_hit, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_v, 64);
+}
+
+// ---- monitor analytics: one fused pass over the rows in HBM ---------------------------------------------------------
+namespace {
+struct StatsArgs {
+  const double *px, *py, *pz, *I, *t, *dx, *dy, *dz, *qre;
+  const int32_t* mon; const unsigned long long* key;
+  long long first, n; int monitor;
+  optb_monitor_frame f;
+  double *stats, *y, *z, *ty, *tz, *wd;
+};
+OPTB_DEV void atomic_min_f64(double* addr, double v) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a;
+  while (v < __longlong_as_double((long long)old)) {
+    const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+OPTB_DEV void atomic_max_f64(double* addr, double v) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a;
+  while (v > __longlong_as_double((long long)old)) {
+    const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+__global__ void stats_init_kernel(double* s) {
+  const int k = threadIdx.x;
+  if (k < OPTB_MS_STRIDE) s[k] = (k == OPTB_MS_MIN_Y || k == OPTB_MS_MIN_Z) ? INFINITY : (k == OPTB_MS_MAX_Y || k == OPTB_MS_MAX_Z) ? -INFINITY : 0.0;
+}
+__global__ void __launch_bounds__(256) monitor_stats_kernel(const StatsArgs a) {
+  __shared__ unsigned int s_hist[OPTB_HIST_BINS];
+  __shared__ double s_red[8][8];
+  if (threadIdx.x < OPTB_HIST_BINS) s_hist[threadIdx.x] = 0u;
+  __syncthreads();
+  double cnt = 0, sI = 0, sy = 0, syy = 0, sz = 0, szz = 0, swd = 0, sty = 0, styty = 0;
+  double ymin = INFINITY, ymax = -INFINITY, zmin = INFINITY, zmax = -INFINITY;
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < a.n; k += (long long)gridDim.x * blockDim.x) {
+    const long long j = a.first + k;
+    bool mine = true;
+    if (a.monitor >= 0) mine = a.mon ? (a.mon[j] == a.monitor) : (int)((a.key[j] >> 24) & 0xffu) == a.monitor;
+    double y = NAN, z = NAN, ty = NAN, tz = NAN, wd = NAN;
+    if (mine) {
+      const double Px = a.px[j], Py = a.py[j], Pz = a.pz[j];
+      y = dot3(Px, Py, Pz, a.f.tangent_y[0], a.f.tangent_y[1], a.f.tangent_y[2]);
+      z = dot3(Px, Py, Pz, a.f.tangent_z[0], a.f.tangent_z[1], a.f.tangent_z[2]);
+      cnt += 1.0; sI += a.I[j]; sy += y; syy = fma(y, y, syy); sz += z; szz = fma(z, z, szz);
+      ymin = fmin(ymin, y); ymax = fmax(ymax, y); zmin = fmin(zmin, z); zmax = fmax(zmax, z);
+      const int b = hist_bin(y, -a.f.half_width, a.f.half_width);
+      if (b >= 0) atomicAdd(&s_hist[b], 1u);
+      if (a.dx) {
+        const double dx = a.dx[j], dy = a.dy[j], dz = a.dz[j];
+        ty = dot3(dx, dy, dz, a.f.tangent_y[0], a.f.tangent_y[1], a.f.tangent_y[2]);
+        tz = dot3(dx, dy, dz, a.f.tangent_z[0], a.f.tangent_z[1], a.f.tangent_z[2]);
+        sty += ty; styty = fma(ty, ty, styty);
+        if (a.qre) {
+          const double dist = a.qre[j] + a.t[j];  // Re(q_at_z(t)) = distance to the waist plane (ray.py:17-25)
+          wd = dot3(dx, dy, dz, a.f.normal[0], a.f.normal[1], a.f.normal[2]) > 0.0 ? -dist : dist;
+          swd += wd;
+        }
+      }
+    }
+    if (a.y) a.y[k] = y;
+    if (a.z) a.z[k] = z;
+    if (a.ty) a.ty[k] = ty;
+    if (a.tz) a.tz[k] = tz;
+    if (a.wd) a.wd[k] = wd;
+  }
+  // block reduction: warp shuffles, then one atomic per block and quantity
+  double v[9] = {cnt, sI, sy, syy, sz, szz, swd, sty, styty};
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    zmin = fmin(zmin, __shfl_xor_sync(0xffffffffu, zmin, o)); zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+  }
+  const int slot[9] = {OPTB_MS_COUNT, OPTB_MS_SUM_I, OPTB_MS_SUM_Y, OPTB_MS_SUM_YY, OPTB_MS_SUM_Z, OPTB_MS_SUM_ZZ,
+                       OPTB_MS_SUM_WD, OPTB_MS_SUM_TY, OPTB_MS_SUM_TYTY};
+  if (lane == 0) {
+    for (int q = 0; q < 8; q++) s_red[q][wid] = q < 8 ? v[q] : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double tot = 0;
+    for (int w = 0; w < 8; w++) tot += s_red[threadIdx.x][w];
+    if (tot != 0.0) atomicAdd(&a.stats[slot[threadIdx.x]], tot);
+  }
+  if (lane == 0) {
+    if (v[8] != 0.0) atomicAdd(&a.stats[OPTB_MS_SUM_TYTY], v[8]);
+    if (ymin <= ymax) { atomic_min_f64(&a.stats[OPTB_MS_MIN_Y], ymin); atomic_max_f64(&a.stats[OPTB_MS_MAX_Y], ymax); }
+    if (zmin <= zmax) { atomic_min_f64(&a.stats[OPTB_MS_MIN_Z], zmin); atomic_max_f64(&a.stats[OPTB_MS_MAX_Z], zmax); }
+  }
+  __syncthreads();
+  if (threadIdx.x < OPTB_HIST_BINS && s_hist[threadIdx.x]) atomicAdd(&a.stats[OPTB_MS_HIST + threadIdx.x], (double)s_hist[threadIdx.x]);
+}
+}  // namespace
+
+extern "C" int optb_monitor_stats(optb_ctx* ctx, const optb_result* rows, int64_t first, int64_t n, int monitor,
+                                  const optb_monitor_frame* frame, double* stats, double* y, double* z, double* ty,
+                                  double* tz, double* waist, void* stream_v) {
+  if (!ctx || !rows || !frame || !stats || first < 0 || n < 0) return -1;
+  if (!rows->hit_px || !rows->hit_py || !rows->hit_pz || !rows->hit_intensity || !rows->hit_t)
+    return fail(ctx, -7, "optb_monitor_stats: hit_px/py/pz, hit_intensity and hit_t are required");
+  if (monitor >= 0 && !rows->hit_monitor && !rows->hit_key) return fail(ctx, -7, "optb_monitor_stats: selecting a monitor needs hit_monitor or hit_key");
+  if ((ty || tz || waist) && !(rows->hit_dx && rows->hit_dy && rows->hit_dz)) return fail(ctx, -7, "optb_monitor_stats: slopes / waist distances need hit_dx, hit_dy, hit_dz");
+  if (waist && !rows->hit_q_re) return fail(ctx, -7, "optb_monitor_stats: waist distances need hit_q_re");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream_v;
+  StatsArgs a;
+  a.px = rows->hit_px; a.py = rows->hit_py; a.pz = rows->hit_pz; a.I = rows->hit_intensity; a.t = rows->hit_t;
+  a.dx = rows->hit_dx && rows->hit_dy && rows->hit_dz ? rows->hit_dx : nullptr; a.dy = rows->hit_dy; a.dz = rows->hit_dz;
+  a.qre = rows->hit_q_re; a.mon = rows->hit_monitor; a.key = (const unsigned long long*)rows->hit_key;
+  a.first = first; a.n = n; a.monitor = monitor; a.f = *frame;
+  a.stats = stats; a.y = y; a.z = z; a.ty = ty; a.tz = tz; a.wd = waist;
+  stats_init_kernel<<<1, 64, 0, st>>>(stats);
+  if (n > 0) {
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
+    monitor_stats_kernel<<<grid, 256, 0, st>>>(a);
+  }
+  CK(cudaGetLastError(), "monitor_stats_kernel");
   return 0;
 }
 

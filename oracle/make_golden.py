@@ -88,7 +88,44 @@ def make_ripa2_post():
     return post
 
 
+ANALYTICS_SCENES = ("doublet", "telescope_4f", "callable_material", "ripa2_simplified")
+
+
+def make_monitor_analytics():
+    """Fixture for the monitor analytics (monitor.py:78-253): the reference's OWN Monitor methods -- sorted accessor
+    views, get_waist_distance, _get_hist_y / std_histy, get_delta_pos, sum / avg intensity -- evaluated by the
+    reference after its own trace, per scene and monitor."""
+    ref = RH.load_reference()
+    d = {}
+    for name in ANALYTICS_SCENES:
+        sc = scenes.REGISTRY[name](ref)
+        table = ref.OpticalTable()
+        table.add_components(sc.components)
+        table.add_monitors(sc.monitors)
+        table.ray_tracing(sc.rays, perfomance_limit=sc.limit)
+        for m, mon in enumerate(table.monitors):
+            if mon.ndata < 2:
+                continue
+            pre = f"{name}__{m}__"
+            d[pre + "yList"], d[pre + "zList"] = mon.get_yList(), mon.get_zList()
+            d[pre + "tYList"], d[pre + "tZList"] = mon.get_tYList(), mon.tZList
+            d[pre + "IList"], d[pre + "tList"] = mon.get_IList(), mon.get_tList()
+            d[pre + "waist_distance"] = mon.get_waist_distance()
+            counts, edges = mon._get_hist_y()
+            d[pre + "hist_counts"], d[pre + "hist_edges"] = counts, edges
+            with np.errstate(all="ignore"):
+                d[pre + "std_histy"] = np.float64(mon.std_histy)
+            dy, dz = mon.get_delta_pos()
+            d[pre + "delta_y"], d[pre + "delta_z"] = dy, dz
+            d[pre + "sum_intensity"], d[pre + "avg_intensity"] = np.float64(mon.sum_intensity), np.float64(mon.avg_intensity)
+    np.savez_compressed(os.path.join(OUT, "monitor_analytics.npz"), **d)
+    return sorted({k.rsplit("__", 1)[0] for k in d})
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["analytics"]:
+        print(make_monitor_analytics())
+        sys.exit(0)
     if sys.argv[1:] == ["abcd"]:
         print(make_abcd()[:2])
         sys.exit(0)

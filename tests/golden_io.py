@@ -9,7 +9,7 @@ from optable_b200.flatten import FlatScene
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-NON_SCENE = {"abcd_4f", "ripa2_post"}  # fixtures of callers, not of a single trace
+NON_SCENE = {"abcd_4f", "ripa2_post", "monitor_analytics"}  # fixtures of callers, not of a single trace
 
 
 def names():

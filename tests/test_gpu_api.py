@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import optable_b200 as ob
+from optable_b200 import _abi as A
 from tests import golden_io, parity, scenes
 
 pytestmark = pytest.mark.gpu
@@ -225,9 +226,8 @@ def test_device_monitor_analytics_match_host_monitor(tmp_path):
         assert float(dm.sum_intensity) == pytest.approx(host.sum_intensity, rel=1e-12)
         assert float(dm.std_histy) == pytest.approx(host.std_histy, rel=1e-12)
         counts, _ = host._get_hist_y()
-        np.testing.assert_array_equal(dm._get_hist_y()[0].cpu().numpy(), counts)
-        dm.hist_y = None                                     # the binning fallback without the trace's histogram
-        np.testing.assert_array_equal(dm._get_hist_y()[0].cpu().numpy(), counts)
+        np.testing.assert_array_equal(dm._get_hist_y()[0], counts)           # the fused kernel's own binning
+        np.testing.assert_array_equal(out["hist_y"][m].cpu().numpy(), counts)  # = the histogram the trace accumulated
         dy, dz = dm.get_delta_pos()
         hy, hz = host.get_delta_pos()
         np.testing.assert_allclose(dy.cpu().numpy(), hy, rtol=0, atol=1e-15)
@@ -291,3 +291,55 @@ def test_component_interact_single_pop_on_device():
                     assert y.alive == x.alive and y.intensity == pytest.approx(x.intensity, rel=1e-9, abs=1e-300)
                     assert y.length == x.length or y.length == pytest.approx(x.length, rel=1e-9)
     assert hits > 10
+
+
+@pytest.mark.parametrize("name", ["doublet", "telescope_4f", "callable_material", "ripa2_simplified"])
+def test_device_monitor_analytics_match_reference_monitor_methods(name):
+    """f2: optable_b200.analytics.DeviceMonitor (fused optb_monitor_stats pass over rows that stay in HBM) against
+    what the REFERENCE's own Monitor methods returned after the reference's own trace (monitor.py:78-253; fixture
+    tests/golden/monitor_analytics.npz, made by oracle/make_golden.py analytics)."""
+    import os
+
+    from optable_b200.analytics import DeviceMonitor
+    from optable_b200.bundle import RayBundle
+    from optable_b200.flatten import pack_rays
+
+    z = np.load(os.path.join(golden_io.GOLDEN_DIR, "monitor_analytics.npz"))
+    sc = scenes.REGISTRY[name](ob)
+    table = ob.OpticalTable()
+    table.add_components(sc.components)
+    table.add_monitors(sc.monitors)
+    arrs, fam_ids, unit = pack_rays(sc.rays)
+    bundle = RayBundle({k: arrs[k] for k in A.RAY_F64}, len(sc.rays))
+    out = table.trace_bundle(bundle, sc.limit)
+    checked = 0
+    q_tol = 1e-6 if name == "telescope_4f" else 1e-9   # waist distances after an ASphere: SURVEY A.11
+    for m, mon in enumerate(table.monitors):
+        pre = f"{name}__{m}__"
+        if pre + "yList" not in z.files:
+            continue
+        dm = DeviceMonitor(mon, out, m)
+        assert dm.ndata == len(z[pre + "yList"]) == dm.stats()["count"]
+        host = lambda t: t.cpu().numpy()
+        np.testing.assert_allclose(host(dm.get_yList()), z[pre + "yList"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(host(dm.get_zList()), z[pre + "zList"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(host(dm.get_tYList()), z[pre + "tYList"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(host(dm.get_tZList()), z[pre + "tZList"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(host(dm.get_IList()), z[pre + "IList"], rtol=1e-9)
+        np.testing.assert_allclose(host(dm.get_tList()), z[pre + "tList"], rtol=1e-9)
+        np.testing.assert_allclose(host(dm.get_waist_distance()), z[pre + "waist_distance"], rtol=q_tol, atol=1e-9)
+        counts, edges = dm._get_hist_y()
+        np.testing.assert_array_equal(counts, z[pre + "hist_counts"])
+        np.testing.assert_allclose(edges, z[pre + "hist_edges"], rtol=0, atol=1e-15)
+        if np.isfinite(z[pre + "std_histy"]):
+            assert dm.std_histy == pytest.approx(float(z[pre + "std_histy"]), rel=1e-12)
+        dy, dz = dm.get_delta_pos()
+        np.testing.assert_allclose(host(dy), z[pre + "delta_y"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(host(dz), z[pre + "delta_z"], rtol=1e-9, atol=1e-12)
+        assert dm.sum_intensity == pytest.approx(float(z[pre + "sum_intensity"]), rel=1e-12)
+        assert dm.avg_intensity == pytest.approx(float(z[pre + "avg_intensity"]), rel=1e-12)
+        st = dm.stats()
+        assert st["min_y"] == pytest.approx(z[pre + "yList"].min(), rel=1e-9, abs=1e-12)
+        assert st["mean_y"] == pytest.approx(z[pre + "yList"].mean(), rel=1e-9, abs=1e-12)
+        checked += 1
+    assert checked >= 1
