@@ -238,7 +238,7 @@ class Engine:
         torch = self.torch
         rs = self._rays_struct(rays_t)
         n = int(rs.n)
-        splitting = scene.flat.max_children > 1 or params.chain_len > 0 or scene.flat.n_capslots > 0
+        splitting = scene.flat.max_children > 1 or params.chain_len > 0 or scene.flat.n_capslots > 0 or params.flag_ambiguity
         live = 0 if not splitting else int(max_live if max_live is not None else max(4 * n, 1024))
         if scene.flat.n_capslots and not params.caps_slack:  # family-serial mode: total FIFO entries over all families
             live = max(live, min(64 * max(n, 16), n * (int(params.max_trace_num) + 2)))
@@ -254,7 +254,7 @@ class Engine:
 
     # -- convenience: exact-size traced result on the host, in reference order -------------------------
     def trace_arrays(self, scene: Scene, arrs, max_trace_num=2000, unit=1e-2, record_segments=True, record_hits=True,
-                     record_hist=False, n_families=None, cap_counts=None, chain_len=0, max_live=None):
+                     record_hist=False, n_families=None, cap_counts=None, chain_len=0, max_live=None, flag_ambiguity=False):
         """Trace a packed ray batch and return numpy result arrays trimmed and sorted to reference order
         (segments by (root, pop); monitor rows by (root, monitor, pop))."""
         torch = self.torch
@@ -276,7 +276,9 @@ class Engine:
         pops_max = n * int(max_trace_num)
         nseg = min(pops_max, 8 * n + 1024) if record_segments else 0
         nhit = min(pops_max * flat.n_monitors, 8 * n + 1024) if record_hits else 0
-        prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families, slack)
+        prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families, slack,
+                               flag_ambiguity)
+        root_flags = torch.zeros(max(n, 1), dtype=torch.int32, device=f"cuda:{self.device}") if flag_ambiguity else None
         np_dt = {torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32}
         # The live ray set of a splitting scene is not known in advance either: a root pops at most max_trace_num rays
         # and every pop queues at most two, so 2 n max_trace_num live rays always suffice; grow towards that bound.
@@ -285,6 +287,8 @@ class Engine:
         retried_rows = False
         while True:
             res, t = self.alloc_result(scene, nseg, nhit, n_families, caps0, slab=True)
+            if root_flags is not None:
+                res.root_flags = root_flags.data_ptr()
             self.trace_device(scene, rays_t, prm, res, live)
             host = None
             if res._slab is not None:  # everything in one copy (synchronises)
@@ -319,6 +323,8 @@ class Engine:
             out = {k: (v[:trim[k]] if k in trim else v).cpu().numpy() for k, v in t.items()}
         for k in A.SEG_U32 + A.HIT_U32:
             out[k] = out[k].view(np.uint32)
+        if root_flags is not None:  # OPTB_AMB_* bits per initial ray, evaluated in-kernel
+            out["root_flags"] = root_flags.cpu().numpy().view(np.uint32)[:n]
         self._raise_status(out["counters"])
         if presorted:
             return out

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liboptb.so")
 SOURCES = ["optb.cu"]
-DEPS = ["optb.cu", "optb_device.cuh", os.path.join("..", "..", "include", "optb.h")]
+DEPS = ["optb.cu", "optb_device.cuh", "optb_flags.cuh", os.path.join("..", "..", "include", "optb.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-ldl",

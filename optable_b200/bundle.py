@@ -160,18 +160,25 @@ def trace_bundle(table, bundle: RayBundle, perfomance_limit=None, record_hits=Tr
                      wavelengths_m=None if wl is None else batch_wavelengths_m(wl, getattr(table, "unit", 1e-2)))
     cap = int(hit_capacity if hit_capacity is not None else bundle.n * max(flat.n_monitors, 1) * 2) if record_hits else 0
     limit = trace_cap(perfomance_limit)
-    dt = DeviceTrace(engine, flat, bundle.n, cap, max_trace_num=limit, record_hist=record_hist, hit_columns=hit_columns)
     rays_t = bundle.to_torch(device=f"cuda:{engine.device}")
     # live-ray budget of a splitting scene: grow on overflow towards the bound 2 n max_trace_num (a root pops at most
-    # max_trace_num rays and each pop queues at most two)
+    # max_trace_num rays and each pop queues at most two); row capacity: the counters keep counting past it, so an
+    # overflowing attempt is repeated once with the exact size
     live, bound = max_live, max(2 * bundle.n * max(limit, 1), 1024)
+    resized = False
     while True:
+        dt = DeviceTrace(engine, flat, bundle.n, cap, max_trace_num=limit, record_hist=record_hist, hit_columns=hit_columns)
         dt.run(rays_t, live)
         cnt = dt.counters()
+        st = int(cnt[A.C_STATUS])
         cur = live if live is not None else max(4 * bundle.n, 1024)
-        if not int(cnt[A.C_STATUS]) & A.ST_WORK_OVERFLOW or cur >= bound:
+        if st & A.ST_WORK_OVERFLOW and cur < bound:
+            live = min(4 * cur, bound)
+        elif st & A.ST_HIT_OVERFLOW and not resized and hit_capacity is None:
+            cap, resized = int(cnt[A.C_HITS]), True
+        else:
             break
-        live = min(4 * cur, bound)
+        dt.scene.close()
     engine._raise_status(cnt)
     nh = int(cnt[A.C_HITS]) if record_hits else 0
     out = {k: dt.t[k][:nh] for k in dt.hit_columns}

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "optb_device.cuh"
+#include "optb_flags.cuh"
 
 using namespace optb;
 
@@ -419,7 +420,8 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
 // SPLIT = some interaction of the scene can emit two rays (or the caller bounded the in-register chain): the
 // wavefront machinery (child slots, per-root generation ranks) is compiled in. Scenes that cannot split run the
 // whole life of a ray in registers with none of it.
-template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT>
+// FLAG = diagnostics variant: the ambiguity mask of SURVEY A.9 is evaluated at every pop (optb_flags.cuh).
+template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = false>
 // Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
 // spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
 // whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
@@ -558,6 +560,10 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
         ray.qim = pk[3 * kBlock]; ray.pl = pk[4 * kBlock]; ray.n = pk[5 * kBlock];
       }
       c_pops++;
+      if constexpr (FLAG) {
+        const unsigned amb = flag_pop(sv, ray, node, t, a.unit);
+        if (amb && a.out.root_flags) atomicOr(&a.out.root_flags[ray.root - a.root_base], amb);
+      }
       // the pop's dead segment: the ray itself when nothing was hit (optical_table.py:132-134), else the
       // truncated copy with length = t, alive = False (optical_component.py:364)
       const bool hit = node >= 0;
@@ -751,6 +757,13 @@ __global__ void sort_prep_kernel(uint32_t* __restrict__ idx, uint32_t* __restric
     const bool solo = (j == 0 || root[slot[j - 1]] != r) && (j == n - 1 || root[slot[j + 1]] != r);
     key_dense[j] = (key[s] & ((1u << key_bits) - 1u)) | ((solo ? 1u : 0u) << key_bits);
   }
+}
+
+__global__ void count_flags_kernel(const uint32_t* __restrict__ flags, long long n, unsigned long long* counters) {
+  unsigned int c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += flags[i] != 0u;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counters[OPTB_C_FLAGGED], (unsigned long long)c);
 }
 
 __global__ void finish_kernel(unsigned long long* counters, unsigned long long gens, unsigned long long launches,
@@ -1062,7 +1075,7 @@ RayBuf make_raybuf(unsigned char* base, long long cap) {
   b.key = (uint32_t*)(base + o);
   return b;
 }
-bool needs_wavefront(const optb_scene* s, const optb_params* p) { return s->max_children > 1 || p->chain_len > 0; }
+bool needs_wavefront(const optb_scene* s, const optb_params* p) { return s->max_children > 1 || p->chain_len > 0 || p->flag_ambiguity; }
 // Interact caps make the result depend on the reference's sequential order as soon as two rays of one family can
 // be in flight: splitting scenes, or several initial rays sharing an `_id` (family column given).
 bool needs_serial(const optb_scene* s, const optb_rays* r, const optb_params* p) {
@@ -1111,13 +1124,14 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   if (prm->record_hits && out->hit_capacity > 0 && !out->hit_monitor && !out->hit_key) return fail(ctx, -7, "record_hits needs hit_monitor or hit_key");
   if (prm->record_hits && out->hit_key && (prm->max_trace_num > (1ll << 24) || scene->n_mons > 256))
     return fail(ctx, -7, "hit_key packs pop into 24 bits and the monitor into 8: max_trace_num <= 2^24 and <= 256 monitors");
-  if (prm->flag_ambiguity) return fail(ctx, -7, "flag_ambiguity: not available in this build");
+  if (prm->flag_ambiguity && !out->root_flags) return fail(ctx, -7, "flag_ambiguity needs result.root_flags [rays.n]");
   if (scene->n_caps > 0 && (!out->cap_counts || prm->n_families < 1)) return fail(ctx, -7, "scene has interact caps: cap_counts/n_families required");
   // cap_counts is [n_capslots][n_families]; without a family column every initial ray is its own family (column
   // index = ray index), so the table must have a column per ray
   if (scene->n_caps > 0 && !rays->family && (long long)prm->n_families < rays->n)
     return fail(ctx, -7, "scene has interact caps and rays.family is NULL: n_families must be >= rays.n");
   const bool serial = needs_serial(scene, rays, prm);
+  if (serial && prm->flag_ambiguity) return fail(ctx, -7, "flag_ambiguity is not available on the family-serial path (binding interact caps)");
   const bool split = !serial && needs_wavefront(scene, prm);
   WsLayout L = ws_layout(rays->n, 0, false);
   long long cap = 0;
@@ -1167,6 +1181,7 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     CK(cudaMemsetAsync(out->hist_yz, 0, sizeof(int64_t) * OPTB_HIST_BINS * OPTB_HIST_BINS * scene->n_mons, st), "memset hist");
   }
 
+  if (prm->flag_ambiguity) CK(cudaMemsetAsync(out->root_flags, 0, sizeof(uint32_t) * (size_t)rays->n, st), "memset root flags");
   TraceArgs a;
   memset(&a, 0, sizeof a);
   a.blob = scene->d_blob; a.blob_bytes = scene->blob_bytes; a.off = scene->off;
@@ -1202,8 +1217,11 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
 #undef OPTB_KROW
 #undef OPTB_K
   static const Kern serial_table[2] = {trace_kernel<false, true, 1, true, true>, trace_kernel<true, true, 1, true, true>};
+  // diagnostics (params.flag_ambiguity): the general variant of the parallel path + the A.9 pass at every pop
+  static const Kern flag_table[2] = {trace_kernel<false, false, 1, true, true, true>, trace_kernel<true, false, 1, true, true, true>};
   Kern kern = serial ? serial_table[scene->in_smem ? 1 : 0]
                      : table[scene->in_smem ? 1 : 0][boxmode][scene->has_asph ? 1 : 0][split ? 1 : 0];
+  if (prm->flag_ambiguity) kern = flag_table[scene->in_smem ? 1 : 0];
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
   int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem), "occupancy");
@@ -1288,6 +1306,10 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     CK(cudaMemcpyAsync(ctx->h_hdr, hdr, sizeof(Header), cudaMemcpyDeviceToHost, st), "read header");
     CK(cudaStreamSynchronize(st), "sync generation");
     n_in = ((Header*)ctx->h_hdr)->n_next;
+  }
+  if (prm->flag_ambiguity && rays->n > 0) {
+    count_flags_kernel<<<(int)std::min<long long>((rays->n + 255) / 256, (long long)full_grid * 4), 256, 0, st>>>(out->root_flags, rays->n, a.counters);
+    launches++;
   }
   finish_kernel<<<1, 1, 0, st>>>(a.counters, gens, launches + 1, hdr);
   CK(cudaGetLastError(), "kernel launch");

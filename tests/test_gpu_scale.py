@@ -245,3 +245,46 @@ def test_lattice_window_walk_equals_reference_walk(engine, case, monkeypatch):
     assert (flat.node_i[:, A.NI_GEOM] == A.G_GRID).any(), "the scene was meant to contain a lattice group"
     got, errs = _both(engine, sc, arrs, limit=limit, max_live=max(40 * len(arrs["ox"]), 1 << 20))
     assert int(got["counters"][A.C_INTERACTIONS]) > len(arrs["ox"]) // 4
+
+
+def test_ambiguity_flags_in_kernel(engine):
+    """SURVEY A.9 on the device (params.flag_ambiguity): rays aimed at an aperture edge, at a shared edge of two
+    coplanar mirrors (equal-distance tie), at grazing incidence and at the TIR threshold get their bits; a clean ray
+    through the middle of everything gets none; OPTB_C_FLAGGED counts the flagged initial rays."""
+    import optable_b200 as ob
+    from optable_b200 import _abi as A
+    from optable_b200.flatten import FlatScene
+
+    m1 = ob.SquareMirror([5, 0.5, 0], width=1, height=1, reflectivity=1.0)       # y in [0, 1]
+    m2 = ob.SquareMirror([5, -0.5, 0], width=1, height=1, reflectivity=1.0)      # y in [-1, 0]: shares the edge y = 0
+    slab = ob.SquareRefractive([9, 5, 0], width=2, height=2, n1=1.0, n2=1.5)     # glass on the -x side
+    sc = scenes.Scene([m1, m2, slab], [], [])
+    crit = np.arcsin(1.0 / 1.5)
+    rays = {
+        "clean": ([0, 0.4, 0.1], [1, 0, 0]),
+        "edge": ([0, 1.0, 0.2], [1, 0, 0]),                       # on the outer edge of m1 -> APERTURE
+        "tie_edge": ([0, 0.0, 0.3], [1, 0, 0]),                   # on the edge shared by m1 and m2 -> APERTURE (+ TIE)
+        "grazing": ([4, 0.3, 0.0], [1e-7, 1.0, 0]),               # skims m1 -> GRAZING
+        "tir": ([8.0, 5.0, 0.0], [np.cos(crit), np.sin(crit), 0]),  # from inside the glass at the critical angle -> TIR
+    }
+    names = list(rays)
+    arrs = scenes.ray_arrays(len(names), [0, 0, 0], [0, 0, 0], [1, 0, 0], [0, 0, 0])
+    for k, nm in enumerate(names):
+        o, d = np.array(rays[nm][0], float), np.array(rays[nm][1], float)
+        d /= np.linalg.norm(d)
+        for j, ax in enumerate("xyz"):
+            arrs["o" + ax][k], arrs["d" + ax][k] = o[j], d[j]
+    arrs["n_medium"][names.index("tir")] = 1.5
+    flat = FlatScene(sc.components, sc.monitors)
+    scene = engine.upload(flat)
+    out = engine.trace_arrays(scene, arrs, max_trace_num=4, flag_ambiguity=True)
+    fl = dict(zip(names, out["root_flags"].tolist()))
+    assert fl["clean"] == 0, fl
+    assert fl["edge"] & A.AMB_APERTURE and fl["tie_edge"] & A.AMB_APERTURE, fl
+    assert fl["grazing"] & A.AMB_GRAZING, fl
+    assert fl["tir"] & A.AMB_TIR, fl
+    assert int(out["counters"][A.C_FLAGGED]) == sum(1 for v in fl.values() if v)
+    # same result with and without the diagnostics pass
+    plain = engine.trace_arrays(scene, arrs, max_trace_num=4)
+    for k in ("seg_leaf", "seg_length", "seg_ox"):
+        np.testing.assert_array_equal(out[k], plain[k])
