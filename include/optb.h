@@ -216,6 +216,13 @@ typedef struct optb_params {
                              segments in (root, pop) order -- the order Monitor.record / OpticalTable.rays have after
                              the reference traced the initial rays one after another -- instead of device append
                              order. Sorted on the device (optb_sort_rows) before the copy back.                  */
+  int32_t reference_roots;/* 1: curved-surface hit distances are the last iterate of the reference's own root finder
+                             (scipy.optimize.brentq with its default xtol = 2e-12, optical_component.py:126-134) run
+                             on the same sign-scan bracket, instead of the closed-form / Newton root the default path
+                             converges to rounding. The two differ by up to 2e-12 (brentq's tolerance), which long
+                             chaotic paths amplify; this mode follows the reference's path, the default one is
+                             faster and closer to the true surface. Decisions (hit index, bounce count) agree. */
+  int32_t reserved;
 } optb_params;
 
 /* Ambiguity bits (the "stated epsilon" of the parity bar): set for an initial ray when, at some pop,

@@ -57,6 +57,7 @@ class Params(C.Structure):
         ("record_segments", C.c_int32), ("record_hits", C.c_int32), ("record_hist", C.c_int32),
         ("chain_len", C.c_int32), ("n_families", C.c_int32), ("caps_slack", C.c_int32),
         ("flag_ambiguity", C.c_int32), ("sorted_rows", C.c_int32),
+        ("reference_roots", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -224,12 +224,13 @@ class Engine:
 
     @staticmethod
     def make_params(max_trace_num=2000, unit=1e-2, record_segments=True, record_hits=True, record_hist=False,
-                    chain_len=0, n_families=1, caps_slack=0, flag_ambiguity=False):
+                    chain_len=0, n_families=1, caps_slack=0, flag_ambiguity=False, reference_roots=False):
         p = A.Params()
         p.max_trace_num, p.unit = int(max_trace_num), float(unit)
         p.record_segments, p.record_hits, p.record_hist = int(record_segments), int(record_hits), int(record_hist)
         p.chain_len, p.n_families, p.caps_slack = int(chain_len), int(n_families), int(caps_slack)
         p.flag_ambiguity = int(bool(flag_ambiguity))
+        p.reference_roots = int(bool(reference_roots))
         return p
 
     def trace_device(self, scene: Scene, rays_t, params: A.Params, result: A.Result, max_live=None, stream=None):
@@ -238,7 +239,7 @@ class Engine:
         torch = self.torch
         rs = self._rays_struct(rays_t)
         n = int(rs.n)
-        splitting = scene.flat.max_children > 1 or params.chain_len > 0 or scene.flat.n_capslots > 0 or params.flag_ambiguity
+        splitting = scene.flat.max_children > 1 or params.chain_len > 0 or scene.flat.n_capslots > 0 or params.flag_ambiguity or params.reference_roots
         live = 0 if not splitting else int(max_live if max_live is not None else max(4 * n, 1024))
         if scene.flat.n_capslots and not params.caps_slack:  # family-serial mode: total FIFO entries over all families
             live = max(live, min(64 * max(n, 16), n * (int(params.max_trace_num) + 2)))
@@ -254,7 +255,8 @@ class Engine:
 
     # -- convenience: exact-size traced result on the host, in reference order -------------------------
     def trace_arrays(self, scene: Scene, arrs, max_trace_num=2000, unit=1e-2, record_segments=True, record_hits=True,
-                     record_hist=False, n_families=None, cap_counts=None, chain_len=0, max_live=None, flag_ambiguity=False):
+                     record_hist=False, n_families=None, cap_counts=None, chain_len=0, max_live=None, flag_ambiguity=False,
+                     reference_roots=False):
         """Trace a packed ray batch and return numpy result arrays trimmed and sorted to reference order
         (segments by (root, pop); monitor rows by (root, monitor, pop))."""
         torch = self.torch
@@ -277,7 +279,7 @@ class Engine:
         nseg = min(pops_max, 8 * n + 1024) if record_segments else 0
         nhit = min(pops_max * flat.n_monitors, 8 * n + 1024) if record_hits else 0
         prm = self.make_params(max_trace_num, unit, record_segments, record_hits, record_hist, chain_len, n_families, slack,
-                               flag_ambiguity)
+                               flag_ambiguity, reference_roots)
         root_flags = torch.zeros(max(n, 1), dtype=torch.int32, device=f"cuda:{self.device}") if flag_ambiguity else None
         np_dt = {torch.float64: np.float64, torch.int64: np.int64, torch.int32: np.int32}
         # The live ray set of a splitting scene is not known in advance either: a root pops at most max_trace_num rays

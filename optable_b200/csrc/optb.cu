@@ -258,7 +258,7 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
 // iterative root solve each) are parked and tested last, when the closest cheap hit is known: a parked asphere
 // whose bracket starts beyond that hit is dismissed without evaluating its profile once. The (t, index) ordering
 // makes the result independent of the visiting order.
-template <bool ASPH>
+template <bool ASPH, bool BRENT = false>
 struct HitSearch {
   const TraceArgs& a; const SceneView& sv; const Ray& ray; bool solo;
   double best_t; int best_node; unsigned int* cnt;  // cnt: this thread's {leaf tests, curved tests, box tests} in smem
@@ -275,7 +275,7 @@ struct HitSearch {
       if (!is_planar_kind(ni[OPTB_NI_GEOM])) atomicAdd(cnt + kBlock, 1u);
       double ox, oy, oz, dx, dy, dz;
       to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
-      t = intersect_leaf<ASPH>(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len, t_beat);
+      t = intersect_leaf<ASPH, BRENT>(sv, ni, nf, ox, oy, oz, dx, dy, dz, ray.len, t_beat);
     }
     if (!(t >= 0.0)) return;
     if (slot >= 0) {  // should_interact / increase_interact_count :136-149
@@ -328,12 +328,12 @@ OPTB_DEV bool grid_window(const double* __restrict__ gd, const Ray& r, int& i0, 
 //        2 = the same walk, and groups whose children form a regular lattice (OPTB_G_GRID: MMA / MLA / DMD arrays)
 //            hand the walk the few children inside the ray's lattice window instead of a descent through their
 //            box hierarchy; each candidate still has to pass the reference's own test of its own box.
-template <int BOXES, bool ASPH>
+template <int BOXES, bool ASPH, bool BRENT = false>
 OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
                           double& best_t, int& best_node, unsigned int* cnt) {
   best_t = INFINITY; best_node = -1;
   const bool no_work = !(ray.flags & OPTB_RF_ALIVE);  // optical_component.py:349-350: a dead ray hits nothing
-  HitSearch<ASPH> hs{a, sv, ray, solo, INFINITY, -1, cnt};
+  HitSearch<ASPH, BRENT> hs{a, sv, ray, solo, INFINITY, -1, cnt};
   unsigned int n_box = 0;
   constexpr int kPark = 4;
   int parked[kPark];
@@ -421,7 +421,9 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
 // wavefront machinery (child slots, per-root generation ranks) is compiled in. Scenes that cannot split run the
 // whole life of a ray in registers with none of it.
 // FLAG = diagnostics variant: the ambiguity mask of SURVEY A.9 is evaluated at every pop (optb_flags.cuh).
-template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = false>
+// BRENT = params.reference_roots: curved-surface roots from the reference's own brentq iteration (brentq_dev) instead
+// of the closed-form / Newton root.
+template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = false, bool BRENT = false>
 // Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
 // spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
 // whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
@@ -509,7 +511,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
           ring_get(a.w, ring + head % a.qcap, ray); head++;
           ray.root = root; ray.family = (int32_t)i; ray.pop = pops++;
           double t; int node;
-          closest_hit<BOXES, ASPH>(a, sv, ray, true, t, node, my_cnt);
+          closest_hit<BOXES, ASPH, BRENT>(a, sv, ray, true, t, node, my_cnt);
           c_pops++;
           const bool hit = node >= 0;
           const int32_t* ni = sv.ni + (hit ? node : 0) * OPTB_NI_STRIDE;
@@ -555,7 +557,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
         volatile double* pk = &s_park[0][threadIdx.x];
         pk[0 * kBlock] = ray.I; pk[1 * kBlock] = ray.wl; pk[2 * kBlock] = ray.qre;
         pk[3 * kBlock] = ray.qim; pk[4 * kBlock] = ray.pl; pk[5 * kBlock] = ray.n;
-        closest_hit<BOXES, ASPH>(a, sv, ray, solo, t, node, my_cnt);
+        closest_hit<BOXES, ASPH, BRENT>(a, sv, ray, solo, t, node, my_cnt);
         ray.I = pk[0 * kBlock]; ray.wl = pk[1 * kBlock]; ray.qre = pk[2 * kBlock];
         ray.qim = pk[3 * kBlock]; ray.pl = pk[4 * kBlock]; ray.n = pk[5 * kBlock];
       }
@@ -1075,7 +1077,9 @@ RayBuf make_raybuf(unsigned char* base, long long cap) {
   b.key = (uint32_t*)(base + o);
   return b;
 }
-bool needs_wavefront(const optb_scene* s, const optb_params* p) { return s->max_children > 1 || p->chain_len > 0 || p->flag_ambiguity; }
+bool needs_wavefront(const optb_scene* s, const optb_params* p) {
+  return s->max_children > 1 || p->chain_len > 0 || p->flag_ambiguity || p->reference_roots;  // (the two modes run the SPLIT variants)
+}
 // Interact caps make the result depend on the reference's sequential order as soon as two rays of one family can
 // be in flight: splitting scenes, or several initial rays sharing an `_id` (family column given).
 bool needs_serial(const optb_scene* s, const optb_rays* r, const optb_params* p) {
@@ -1222,6 +1226,13 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   Kern kern = serial ? serial_table[scene->in_smem ? 1 : 0]
                      : table[scene->in_smem ? 1 : 0][boxmode][scene->has_asph ? 1 : 0][split ? 1 : 0];
   if (prm->flag_ambiguity) kern = flag_table[scene->in_smem ? 1 : 0];
+  // params.reference_roots: the general variants with brentq_dev (parallel and family-serial)
+  static const Kern brent_table[2][2] = {{trace_kernel<false, false, 1, true, true, false, true>, trace_kernel<true, false, 1, true, true, false, true>},
+                                         {trace_kernel<false, true, 1, true, true, false, true>, trace_kernel<true, true, 1, true, true, false, true>}};
+  if (prm->reference_roots) {
+    if (prm->flag_ambiguity) return fail(ctx, -7, "reference_roots and flag_ambiguity are separate diagnostics modes");
+    kern = brent_table[serial ? 1 : 0][scene->in_smem ? 1 : 0];
+  }
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
   int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem), "occupancy");

@@ -242,6 +242,17 @@ struct AsphF {
     }
     return fma(R, sqrt(fma(k1, r2, 1.0)) - 1.0, Px);
   }
+  // Surface.f itself (surfaces.py:375-378), not rescaled: what scipy's brentq sees in the reference (its secant /
+  // inverse-quadratic steps depend on the values of f, not only on its zeros)
+  OPTB_DEV double truef(double t) const {
+    double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+    double r2 = fma(Py, Py, Pz * Pz);
+    if (form == OPTB_ASPH_PARAMETRIC) {
+      double s = sqrt(fma(-k1, r2, 1.0));
+      return Px + r2 / (R * (1.0 + s)) + r2 * r2 * fma(r2, fma(r2, a8, a6), a4);
+    }
+    return fma(R, sqrt(fma(k1, r2, 1.0)) - 1.0, Px);
+  }
   // g and dg/dt at t (for the Newton refinement of a bracketed root)
   OPTB_DEV void eval2(double t, double& g, double& dg) const {
     double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
@@ -304,6 +315,65 @@ OPTB_DEV double newton_bracketed(const F& f, double lo, double hi, double glo, d
   return x;
 }
 
+// scipy.optimize.brentq (scipy/optimize/Zeros/brentq.c; xtol = 2e-12, rtol = 4 eps, maxiter = 100: the defaults the
+// reference calls it with, optical_component.py:132) restated for the device. The reference's hit distance on a curved
+// surface IS this iteration's last iterate, up to 2e-12 away from the true root; with `reference_roots` the device
+// runs the same iteration on the same bracket and lands on the same iterate (to the rounding of f), instead of on the
+// root itself. f(xa) f(xb) < 0 is guaranteed by the caller (the sign scan).
+template <class F>
+OPTB_DEV double brentq_dev(const F& f, double xa, double xb) {
+  const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+  double xpre = xa, xcur = xb, xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
+  double fpre = f(xpre), fcur = f(xcur);
+  if (fpre == 0.0) return xpre;
+  if (fcur == 0.0) return xcur;
+  for (int it = 0; it < 100; it++) {
+    if (fpre != 0.0 && fcur != 0.0 && (signbit(fpre) != signbit(fcur))) {
+      xblk = xpre; fblk = fpre;
+      spre = scur = xcur - xpre;
+    }
+    if (fabs(fblk) < fabs(fcur)) {
+      xpre = xcur; xcur = xblk; xblk = xpre;
+      fpre = fcur; fcur = fblk; fblk = fpre;
+    }
+    const double delta = (xtol + rtol * fabs(xcur)) / 2;
+    const double sbis = (xblk - xcur) / 2;
+    if (fcur == 0.0 || fabs(sbis) < delta) return xcur;
+    if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+      double stry;
+      if (xpre == xblk) {
+        stry = -fcur * (xcur - xpre) / (fcur - fpre);                       // secant
+      } else {
+        const double dpre = (fpre - fcur) / (xpre - xcur), dblk = (fblk - fcur) / (xblk - xcur);
+        stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));  // inverse quadratic
+      }
+      if (2 * fabs(stry) < fmin(fabs(spre), 3 * fabs(sbis) - delta)) { spre = scur; scur = stry; }
+      else { spre = sbis; scur = sbis; }
+    } else {
+      spre = sbis; scur = sbis;
+    }
+    xpre = xcur; fpre = fcur;
+    if (fabs(scur) > delta) xcur += scur;
+    else xcur += (sbis > 0 ? delta : -delta);
+    fcur = f(xcur);
+  }
+  return xcur;
+}
+
+// Surface.f along a local ray for the quadric kinds (surfaces.py:224-225, 294-295), as brentq_dev's functor
+struct QuadF {
+  int cyl; double R, ox, oy, oz, dx, dy, dz;
+  OPTB_DEV double operator()(double t) const {
+    const double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+    return sqrt(cyl ? fma(Px, Px, Py * Py) : dot3(Px, Py, Pz, Px, Py, Pz)) - R;
+  }
+};
+template <class F>
+struct TrueF {  // adapts AsphF::truef to operator()
+  const F& f;
+  OPTB_DEV double operator()(double t) const { return f.truef(t); }
+};
+
 // np.linspace(a, b, 10)[i]
 OPTB_DEV double sample_t(int i, double a, double b, double step) {
   // (double)i from a constant table: avoids an I2F.F64 per sample
@@ -359,7 +429,7 @@ OPTB_DEV double intersect_planar(const SceneView& sv, const int32_t* __restrict_
 }
 
 // intersect_point_local optical_component.py:197-233 (curved branch) for one leaf, local-frame ray. Returns t or -1.
-template <bool ASPH>
+template <bool ASPH, bool BRENT = false>
 OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
                                double ox, double oy, double oz, double dx, double dy, double dz, double len,
                                double t_beat = INFINITY) {
@@ -435,8 +505,8 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
       bool solve = true;
       double lo = ta;
       if (asc) {
-        if (tb <= 1e-9 || ta > len) solve = false;  // every root in here fails t >= EPS (or t <= length)
-        else if (ta < 1e-9) {
+        if ((BRENT ? tb < 1e-9 : tb <= 1e-9) || ta > len) solve = false;  // every root in here fails t >= EPS (or t <= length)
+        else if (!BRENT && ta < 1e-9) {
           // The sub-interval straddles the admissibility threshold (the usual case right after leaving this
           // very surface: the root is the self-intersection at t ~ 0). One sample at t = EPS tells on which
           // side the root lies; below it the reference finds it with brentq and then filters it out.
@@ -446,7 +516,7 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
         }
       }
       if (solve) {
-        double r = newton_bracketed(f, lo, tb, f(lo), f(tb));
+        double r = BRENT ? brentq_dev(TrueF<AsphF>{f}, ta, tb) : newton_bracketed(f, lo, tb, f(lo), f(tb));
         if (r >= 1e-9 && r <= len) {
           double Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
           const double rmax = p[0] + 1e-12;
@@ -500,7 +570,11 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
     chg &= chg - 1u;
     // exactly one root of g inside this sub-interval: entering (g: + -> -, seen along increasing t) is `lo`
     const bool ga_pos = (pos >> i) & 1u;
-    const double r = (A != 0.0) ? ((ga_pos == asc) ? lo : hi) : lo;
+    double r = (A != 0.0) ? ((ga_pos == asc) ? lo : hi) : lo;
+    if (BRENT && A != 0.0) {  // the reference's own iterate on this sub-interval instead of the closed-form root
+      const QuadF qf{g == OPTB_G_CYL, p[0], ox, oy, oz, dx, dy, dz};
+      r = brentq_dev(qf, sample_t(i, a, b, step), sample_t(i + 1, a, b, step));
+    }
     if (r >= 1e-9 && r <= len) {
       double Px = fma(r, dx, ox), Py = fma(r, dy, oy), Pz = fma(r, dz, oz);
       if (curved_within(sv, g, ni, p, Px, Py, Pz)) {

@@ -77,14 +77,20 @@ OPTB_DEV unsigned flag_pop(const SceneView& sv, const Ray& ray, int best_node, d
   const double t_rel = (best_node >= 0) ? best_t * (1.0 + eps) : INFINITY;  // candidates beyond cannot matter
   int i = 0;
   const int n = sv.n_nodes;
+  // A box test decided by less than the margin only matters if something under that box could be hit: such boxes are
+  // entered either way, and the SLAB bit is set when a leaf below them yields a candidate (a ray leaving a surface
+  // starts ON that surface's box -- t2 = +-1 ulp -- and the surface's own leaf test then fails t >= 1e-9: no bit).
+  int marginal_until = 0;
   while (i < n) {
     const double* tv = sv.trav + i * 8;
     const int2 gs = *reinterpret_cast<const int2*>(tv + 6);
     if (*reinterpret_cast<const int*>(tv + 7)) {
       double t1, t2;
-      const bool hit = flag_slab(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, tv, t1, t2, amb);
-      if (near(t2 + 1e-12 - t1, 1e-11) || near(t2, 1e-11)) amb |= OPTB_AMB_SLAB;
-      if (!hit) { i = gs.y; continue; }
+      unsigned box_amb = 0u;
+      const bool hit = flag_slab(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, tv, t1, t2, box_amb);
+      const bool marginal = box_amb != 0u || near(t2 + 1e-12 - t1, 1e-11) || near(t2, 1e-11);
+      if (marginal) marginal_until = max(marginal_until, gs.y);
+      else if (!hit) { i = gs.y; continue; }
     }
     const int g = gs.x;
     const int cur = i++;
@@ -158,6 +164,7 @@ OPTB_DEV unsigned flag_pop(const SceneView& sv, const Ray& ray, int best_node, d
       }
       if (!(t >= 0.0)) continue;
     }
+    if (cur < marginal_until && t <= t_rel) amb |= OPTB_AMB_SLAB;  // a candidate that exists only if a marginal box passes
     // a second surface as close as the winner (the reference decides by the last bit of t; ties go to list order)
     if (best_node >= 0 && cur != best_node && near(t - best_t, eps * fmax(fabs(best_t), 1e-3))) amb |= OPTB_AMB_TIE;
   }

@@ -37,7 +37,7 @@ def test_library_exports_all_symbols():
 def test_struct_sizes():
     assert ctypes.sizeof(A.SceneDesc) == 6 * 4 + 8 + 6 * 8
     assert ctypes.sizeof(A.Rays) == 8 + 15 * 8 + 8
-    assert ctypes.sizeof(A.Params) == 8 + 8 + 8 * 4
+    assert ctypes.sizeof(A.Params) == 8 + 8 + 10 * 4
     assert ctypes.sizeof(A.Result) == 2 * 8 + (13 + 3 + 1 + 1 + 2 + 10 + 2) * 8 + 4 * 8
 
 

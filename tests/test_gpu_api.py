@@ -319,7 +319,7 @@ def test_device_monitor_analytics_match_reference_monitor_methods(name):
         if pre + "yList" not in z.files:
             continue
         dm = DeviceMonitor(mon, out, m)
-        assert dm.ndata == len(z[pre + "yList"]) == dm.stats()["count"]
+        assert dm.ndata == len(z[pre + "yList"]) == dm.stats()["count"], (dm.ndata, len(z[pre + "yList"]), dm.stats()["count"], out["counters"])
         host = lambda t: t.cpu().numpy()
         np.testing.assert_allclose(host(dm.get_yList()), z[pre + "yList"], rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(host(dm.get_zList()), z[pre + "zList"], rtol=1e-9, atol=1e-12)

@@ -264,7 +264,7 @@ def test_ambiguity_flags_in_kernel(engine):
         "clean": ([0, 0.4, 0.1], [1, 0, 0]),
         "edge": ([0, 1.0, 0.2], [1, 0, 0]),                       # on the outer edge of m1 -> APERTURE
         "tie_edge": ([0, 0.0, 0.3], [1, 0, 0]),                   # on the edge shared by m1 and m2 -> APERTURE (+ TIE)
-        "grazing": ([4, 0.3, 0.0], [1e-7, 1.0, 0]),               # skims m1 -> GRAZING
+        "grazing": ([5 - 2e-8, 0.2, 0.0], [1e-7, 1.0, 0]),        # skims m1 (meets it at y = 0.4) -> GRAZING
         "tir": ([8.0, 5.0, 0.0], [np.cos(crit), np.sin(crit), 0]),  # from inside the glass at the critical angle -> TIR
     }
     names = list(rays)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """CUDA vs oracle on many random scenes (tests/scenes.fuzz):
-  python tools/fuzz_sweep.py FIRST_SEED N_SCENES [n_rays] [--extended] [--caps]
+  python tools/fuzz_sweep.py FIRST_SEED N_SCENES [n_rays] [--extended] [--caps] [--reference-roots]
 (on the GPU so far: 300 --extended scenes, 40 --caps scenes; see profiles/r1_parity_sweep.md)"""
 import os, sys, time, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,6 +16,7 @@ argv = [a for a in sys.argv[1:] if not a.startswith("--")]
 first, count = int(argv[0]), int(argv[1])
 n_rays = int(argv[2]) if len(argv) > 2 else 64
 EXTENDED, CAPS = "--extended" in flags, "--caps" in flags
+KW = {"reference_roots": True} if "--reference-roots" in flags else {}   # curved roots from the device's brentq restatement
 e = Engine.get(0)
 pops = rays = hits = 0
 flagged, failures, worst = [], [], collections.defaultdict(float)
@@ -29,7 +30,7 @@ for seed in range(first, first + count):
     prm = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam))
     raw = O.trace(flat, arrs, **prm)
     want = RH.arrays_from_result(raw)
-    got = RH.arrays_from_result(e.trace_arrays(e.upload(flat), arrs, **prm))
+    got = RH.arrays_from_result(e.trace_arrays(e.upload(flat), arrs, **prm, **KW))
     for c in sc.components:
         kinds[type(c).__name__] += 1
     try:
@@ -41,7 +42,7 @@ for seed in range(first, first + count):
         batch = parity.restart_batch(raw, np.nonzero(np.isinf(arrs["length"]))[0])
         p1 = dict(max_trace_num=3, unit=unit, n_families=len(batch["ox"]))
         want1 = RH.arrays_from_result(O.trace(flat, batch, **p1))
-        got1 = RH.arrays_from_result(e.trace_arrays(e.upload(flat), batch, **p1))
+        got1 = RH.arrays_from_result(e.trace_arrays(e.upload(flat), batch, **p1, **KW))
         errs1, ties1 = parity.compare_flagging_ties(flat, want1, got1, q_rtol=1e-5 if parity.q_rtol_for(flat) > parity.RTOL else parity.RTOL, label=f"seed {seed} restarted")
         for k, v in errs1.items():
             worst1[k] = max(worst1[k], float(v))
