@@ -333,6 +333,14 @@ const char* optb_last_error(const optb_ctx* ctx);
 int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* desc, optb_scene** out);
 int optb_scene_destroy(optb_ctx* ctx, optb_scene* scene);
 
+/* Rewrite the rows of the listed nodes of an uploaded scene from `desc` (the tables the scene was uploaded from, with
+ * those rows changed in place: same node count, kinds, skip pointers, materials and aux pool). What a GUI loop needs
+ * when one component moved (optable/interact.py:455-457 re-runs the user's script per slider event): a few hundred
+ * bytes go to the device instead of the whole scene, the scene handle -- and any CUDA graph captured over traces of
+ * it -- stays valid. Stream-ordered on `stream`.                                                                 */
+int optb_scene_update_nodes(optb_ctx* ctx, optb_scene* scene, const optb_scene_desc* desc,
+                            const int32_t* nodes, int32_t n_nodes, void* stream);
+
 /* Bytes of device workspace optb_trace needs for `n_rays` roots when at most
  * `max_live` rays are alive at once (max_live >= n_rays).                             */
 int64_t optb_workspace_bytes(const optb_scene* scene, int64_t n_rays, int64_t max_live);

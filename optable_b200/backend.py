@@ -86,6 +86,16 @@ class Scene:
         engine._check(lib().optb_scene_upload(engine._ctx, C.byref(desc), C.byref(h)))
         self._h = h
 
+    def update_nodes(self, nodes, stream=None):
+        """Send the rows of `nodes` (FlatScene.refresh's return value) of the already updated `self.flat` tables to
+        the device copy of the scene (optb_scene_update_nodes): the handle, and CUDA graphs captured over it, stay valid."""
+        L = lib()
+        L.optb_scene_update_nodes.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(A.SceneDesc), C.c_void_p, C.c_int32, C.c_void_p]
+        idx = np.ascontiguousarray(nodes, dtype=np.int32)
+        desc = self.flat.desc()
+        st = self.engine.torch.cuda.current_stream(self.engine.device).cuda_stream if stream is None else stream
+        self.engine._check(L.optb_scene_update_nodes(self.engine._ctx, self._h, C.byref(desc), idx.ctypes.data, len(idx), C.c_void_p(st)))
+
     def close(self):
         if self._h:
             lib().optb_scene_destroy(self.engine._ctx, self._h)

@@ -139,6 +139,30 @@ class DeviceTrace:
             self.t["cap_counts"].zero_()  # a bundle is a fresh set of ray ids every time
         self.engine.trace_device(self.scene, rays_t, self.prm, self.res, max_live)
 
+    def capture(self, rays_t, max_live=None):
+        """Capture one `run` on `rays_t` into a CUDA graph (scenes that cannot split rays: their whole bounce loop
+        is a fixed sequence of launches). `replay()` then re-issues it with one driver call; the ray columns, the
+        result buffers and the scene blob are read at replay time, so the caller may overwrite the rays in place
+        and move components with `scene.update_nodes(flat.refresh(component))` between replays."""
+        torch = self.torch
+        if self.flat.max_children > 1 or self.prm.chain_len > 0 or self.flat.n_capslots:
+            raise NotImplementedError("CUDA-graph replay needs a scene whose interactions emit one ray at most (no host round trips)")
+        self.run(rays_t, max_live)          # warm-up: workspace and kernel attributes exist before the capture
+        torch.cuda.synchronize()
+        self._graph_rays = rays_t
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.run(rays_t, max_live)
+        return self
+
+    def replay(self):
+        self._graph.replay()
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        self._graph = None
+        self.scene.close()
+
     def counters(self):
         return self.t["counters"].cpu().numpy()
 

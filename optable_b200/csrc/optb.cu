@@ -1015,6 +1015,43 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   return 0;
 }
 
+extern "C" int optb_scene_update_nodes(optb_ctx* ctx, optb_scene* s, const optb_scene_desc* d, const int32_t* nodes,
+                                       int32_t n, void* stream_v) {
+  if (!ctx || !s || !d || (n > 0 && !nodes)) return -1;
+  if (d->n_nodes != s->n_nodes || d->n_leaves != s->n_leaves || d->n_materials != s->n_mats || d->n_aux != s->n_aux ||
+      d->n_capslots != s->n_caps)
+    return fail(ctx, -5, "optb_scene_update_nodes: the tables no longer have the shape of the uploaded scene");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream_v;
+  for (int k = 0; k < n; k++) {
+    const int i = nodes[k];
+    if (i < 0 || i >= d->n_nodes) return fail(ctx, -5, "optb_scene_update_nodes: node index out of range");
+    const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
+    const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
+    CK(cudaMemcpyAsync(s->d_blob + s->off.nf + (size_t)i * OPTB_NF_STRIDE * 8, nf, OPTB_NF_STRIDE * 8, cudaMemcpyHostToDevice, st), "update node_f");
+    CK(cudaMemcpyAsync(s->d_blob + s->off.ni + (size_t)i * OPTB_NI_STRIDE * 4, ni, OPTB_NI_STRIDE * 4, cudaMemcpyHostToDevice, st), "update node_i");
+    CK(cudaMemcpyAsync(s->d_blob + s->off.trav + (size_t)i * 64, nf + OPTB_NF_AABB, 48, cudaMemcpyHostToDevice, st), "update box");
+  }
+  // scene-wide properties that pick the kernel variant follow the new rows
+  int mc = 0, boxes = 0, asph = 0;
+  for (int i = 0; i < d->n_nodes; i++) {
+    const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
+    const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
+    if (ni[OPTB_NI_AABB]) boxes = 1;
+    if (ni[OPTB_NI_GEOM] == OPTB_G_ASPHERE) asph = 1;
+    int k = 0;
+    switch (ni[OPTB_NI_INTER]) {
+      case OPTB_I_MIRROR: k = (nf[OPTB_NF_REFL] > 0) + (nf[OPTB_NF_TRANS] > 0); break;
+      case OPTB_I_REFRACT: k = nf[OPTB_NF_REFL] > 0 ? 2 : 1; break;
+      case OPTB_I_THINLENS: k = 1; break;
+      default: k = 0;
+    }
+    mc = std::max(mc, k);
+  }
+  s->max_children = mc; s->has_boxes = boxes; s->has_asph = asph;
+  return 0;
+}
+
 extern "C" int optb_scene_destroy(optb_ctx* ctx, optb_scene* s) {
   if (!s) return 0;
   if (ctx) cudaSetDevice(ctx->device);
@@ -1324,8 +1361,12 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   }
   finish_kernel<<<1, 1, 0, st>>>(a.counters, gens, launches + 1, hdr);
   CK(cudaGetLastError(), "kernel launch");
-  CK(cudaEventRecord(scene->last_use, st), "record scene use");
-  const_cast<optb_scene*>(scene)->used = true;
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &capturing);
+  if (capturing == cudaStreamCaptureStatusNone) {  // (a captured event could not be waited on when the scene is released;
+    CK(cudaEventRecord(scene->last_use, st), "record scene use");  //  the owner of a graph synchronises before that)
+    const_cast<optb_scene*>(scene)->used = true;
+  }
   return 0;
 }
 

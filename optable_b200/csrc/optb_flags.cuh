@@ -14,26 +14,40 @@ namespace optb {
 
 OPTB_DEV bool near(double x, double eps) { return fabs(x) <= eps; }
 
-// general slab test with margins (solver.py:5-48); returns hit, sets SLAB when the decision is marginal
+// general slab test with margins (solver.py:5-48); returns hit, sets SLAB in `amb` when the decision is marginal:
+// an axis within 1e-10 of the np.isclose "parallel" threshold, a parallel axis whose origin sits on a box face, or the
+// entry parameter of one axis within 1e-11 of the (1e-12-slackened) exit parameter of ANOTHER axis. Entry and exit of
+// the same axis are not compared: for a zero-thickness box (the lab box of an unrotated planar leaf) they are the same
+// number computed twice, which is what the reference's 1e-12 slack is there for, and nothing hinges on rounding.
 OPTB_DEV bool flag_slab(double ox, double oy, double oz, double dx, double dy, double dz, const double* __restrict__ bb,
                         double& t1o, double& t2o, unsigned& amb) {
   double t1 = 0.0, t2 = INFINITY;
   const double o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+  double tn[3], tf[3];
+  bool par[3];
 #pragma unroll
   for (int ax = 0; ax < 3; ax++) {
     const double bmin = bb[2 * ax], bmax = bb[2 * ax + 1];
     if (near(fabs(d[ax]) - 1e-8, 1e-10)) amb |= OPTB_AMB_SLAB;
-    if (fabs(d[ax]) <= 1e-8) {
+    par[ax] = fabs(d[ax]) <= 1e-8;
+    tn[ax] = 0.0; tf[ax] = INFINITY;
+    if (par[ax]) {
       const double scale = 1e-11 * fmax(1.0, fmax(fabs(bmin), fabs(bmax)));
       if (near(o[ax] - bmin, scale) || near(o[ax] - bmax, scale)) amb |= OPTB_AMB_SLAB;
       if (o[ax] < bmin || o[ax] > bmax) { t1 = 1.0; t2 = 0.0; }
     } else {
       const double inv = 1.0 / d[ax];
       const double ta = (bmin - o[ax]) * inv, tb = (bmax - o[ax]) * inv;
-      t1 = fmax(t1, fmin(ta, tb));
-      t2 = fmin(t2, fmax(ta, tb));
+      tn[ax] = fmin(ta, tb); tf[ax] = fmax(ta, tb);
+      t1 = fmax(t1, tn[ax]);
+      t2 = fmin(t2, tf[ax]);
     }
   }
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++)
+#pragma unroll
+    for (int bx = 0; bx < 3; bx++)
+      if (ax != bx && !par[ax] && !par[bx] && near(tf[bx] + 1e-12 - tn[ax], 1e-11)) amb |= OPTB_AMB_SLAB;
   t1o = t1; t2o = t2;
   return (t2 + 1e-12 >= t1) && (t2 >= 0.0);
 }
@@ -88,7 +102,7 @@ OPTB_DEV unsigned flag_pop(const SceneView& sv, const Ray& ray, int best_node, d
       double t1, t2;
       unsigned box_amb = 0u;
       const bool hit = flag_slab(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, tv, t1, t2, box_amb);
-      const bool marginal = box_amb != 0u || near(t2 + 1e-12 - t1, 1e-11) || near(t2, 1e-11);
+      const bool marginal = box_amb != 0u || near(t2, 1e-11);  // (t2 ~ 0: the ray starts on the box)
       if (marginal) marginal_until = max(marginal_until, gs.y);
       else if (!hit) { i = gs.y; continue; }
     }
@@ -132,9 +146,9 @@ OPTB_DEV unsigned flag_pop(const SceneView& sv, const Ray& ray, int best_node, d
       else if (g == OPTB_G_CYL) { bb[0] = -p[0]; bb[1] = p[0]; bb[2] = -p[0]; bb[3] = p[0]; bb[4] = -p[1] / 2; bb[5] = p[1] / 2; }
       else { const double* rec = sv.aux + ni[OPTB_NI_AUX]; for (int k = 0; k < 6; k++) bb[k] = rec[13 + k]; }
       double t1, t2;
-      flag_slab(ox, oy, oz, dx, dy, dz, bb, t1, t2, amb);
-      if (near(t2 + 1e-9 - t1, 1e-11)) amb |= OPTB_AMB_SLAB;
-      if (t2 + 1e-9 < t1) continue;
+      unsigned loc_amb = 0u;
+      flag_slab(ox, oy, oz, dx, dy, dz, bb, t1, t2, loc_amb);
+      if (t2 + 1e-9 < t1) { if (near(t2 + 1e-9 - t1, 1e-11)) amb |= OPTB_AMB_SLAB; continue; }
       if (near(t2 - 100.0, 1e-7)) amb |= OPTB_AMB_SCAN;
       t1 = fmax(t1, 0.0); t2 = fmin(t2, 100.0);
       const double a = t1 - 1e-9, b = t2 + 1e-9, step = (b - a) / 9.0;

@@ -144,6 +144,8 @@ class FlatScene:
         self.capslots = []     # cap slot -> component object
         self.max_children = 0  # most rays one interaction can emit (<=1: no splitting anywhere)
         self._pending_inv = []
+        self._row_owner = {}   # id(node_i row) -> the component object that produced it (refresh)
+        self._node_of = {}     # id(component) -> node index
         self._grids = []       # (aux offset of the cell table, [child node_i rows in list order]) per lattice group
         for c in components:
             tree = self._visit(c, in_group=False)
@@ -152,16 +154,9 @@ class FlatScene:
         for off, rows in self._grids:  # node indices are only known after emission
             self._aux[off:off + len(rows)] = [float(r[A.NI_SKIP] - 1) for r in rows]  # a leaf skips to index + 1
         del self._grids
-        if self._pending_inv:
-            # np.linalg.inv on the stack runs the same per-matrix LAPACK solve as the reference's call per
-            # component (optical_component.py:108): identical bits, ~30x less Python overhead
-            Ts = np.array([nf[A.NF_T:A.NF_T + 9] for _, nf in self._pending_inv], dtype=np.float64).reshape(-1, 3, 3)
-            Tinvs = np.linalg.inv(Ts)
-            ortho = np.abs(Tinvs @ Tinvs.transpose(0, 2, 1) - np.identity(3)).max(axis=(1, 2)) < 1e-14
-            for (ni, nf), Ti, flag in zip(self._pending_inv, Tinvs.reshape(-1, 9).tolist(), ortho.tolist()):
-                nf[A.NF_TINV:A.NF_TINV + 9] = Ti
-                ni[A.NI_ORTHO] = int(flag)
-        del self._pending_inv
+        self._finish_inverses()
+        self._owner_of_node = {i: self._row_owner[id(r)] for i, r in enumerate(self._ni) if id(r) in self._row_owner}
+        del self._row_owner
         self.node_i = np.ascontiguousarray(np.array(self._ni, dtype=np.int32).reshape(-1, A.NI_STRIDE))
         self.node_f = np.ascontiguousarray(np.array(self._nf, dtype=np.float64).reshape(-1, A.NF_STRIDE))
         self.mat_kind = np.array(self._mats.kind or [0], dtype=np.int32)
@@ -183,6 +178,103 @@ class FlatScene:
         self.n_materials = int(self.mat_kind.shape[0])  # >= 1 (a dummy row when nothing refracts)
         self.n_monitors = len(self.monitors)
         self.n_capslots = len(self.capslots)
+
+    def _finish_inverses(self):
+        if self._pending_inv:
+            # np.linalg.inv on the stack runs the same per-matrix LAPACK solve as the reference's call per
+            # component (optical_component.py:108): identical bits, ~30x less Python overhead
+            Ts = np.array([nf[A.NF_T:A.NF_T + 9] for _, nf in self._pending_inv], dtype=np.float64).reshape(-1, 3, 3)
+            Tinvs = np.linalg.inv(Ts)
+            ortho = np.abs(Tinvs @ Tinvs.transpose(0, 2, 1) - np.identity(3)).max(axis=(1, 2)) < 1e-14
+            for (ni, nf), Ti, flag in zip(self._pending_inv, Tinvs.reshape(-1, 9).tolist(), ortho.tolist()):
+                nf[A.NF_TINV:A.NF_TINV + 9] = Ti
+                ni[A.NI_ORTHO] = int(flag)
+        self._pending_inv = []
+
+    # -- incremental re-flatten (the GUI loop moves ONE component per slider event) ----------
+    def refresh(self, component):
+        """Re-read one component (leaf, or group without a synthetic box hierarchy) after its pose or parameters
+        changed, rewrite its rows of the tables in place and re-read the cached boxes of its ancestor groups (the
+        reference's groups keep their own, possibly stale, `.bbox`: SURVEY A.2 -- whatever the objects say is what
+        gets flattened). Returns the list of node indices whose rows changed (for Scene.update_nodes), or None when
+        the change cannot be expressed in place (topology, materials, polygons, lattice descriptors or cap slots would
+        move): the caller then builds a new FlatScene."""
+        first = self._node_of.get(id(component))
+        if first is None:
+            return None
+        end = int(self.node_i[first, A.NI_SKIP])
+        owners = self._owner_of_node
+        if any(i not in owners for i in range(first, end)) or (self.node_i[first:end, A.NI_GEOM] == A.G_GRID).any():
+            return None   # synthetic wrappers / lattice inside: rebuild
+        in_group = bool(self.node_i[first, A.NI_AABB]) if self.node_i[first, A.NI_GEOM] not in (A.G_GROUP, A.G_GRID) else first in self._parents()
+        # re-visit into scratch lists with the bookkeeping of this scene (materials, aux, leaves, caps must not grow)
+        keep = (self._ni, self._nf, self.leaves, self.capslots, len(self._aux), len(self._mats.kind))
+        self._ni, self._nf, self.leaves, self.capslots = [], [], list(self.leaves), list(self.capslots)
+        self._row_owner, node_of_backup = {}, dict(self._node_of)
+        n_leaves0, n_caps0 = len(self.leaves), len(self.capslots)
+        try:
+            tree = self._visit(component, in_group=in_group)
+            if tree is None:
+                return None
+            self._emit(tree)
+            self._finish_inverses()
+            new_i = np.array(self._ni, dtype=np.int32).reshape(-1, A.NI_STRIDE)
+            new_f = np.array(self._nf, dtype=np.float64).reshape(-1, A.NF_STRIDE)
+            grew = len(self._aux) != keep[4] or len(self._mats.kind) != keep[5] or len(self.capslots) != n_caps0 + int((new_i[:, A.NI_CAPSLOT] >= 0).sum())
+        finally:
+            new_leaves = self.leaves[n_leaves0:]
+            self._ni, self._nf, self.leaves, self.capslots = keep[0], keep[1], keep[2], keep[3]
+            del self._aux[keep[4]:]
+            self._node_of = node_of_backup
+            self._row_owner = {}
+        old_i = self.node_i[first:end]
+        if grew or new_i.shape[0] != end - first or not np.array_equal(new_i[:, A.NI_GEOM], old_i[:, A.NI_GEOM]):
+            return None
+        # keep the global numbering of the old rows (skip pointers, dense leaf numbers, cap slots)
+        new_i[:, A.NI_SKIP] += first
+        new_i[:, A.NI_LEAF] = old_i[:, A.NI_LEAF]
+        new_i[:, A.NI_CAPSLOT] = old_i[:, A.NI_CAPSLOT]
+        if not np.array_equal(new_i[:, [A.NI_AUX, A.NI_MAT1, A.NI_MAT2]], old_i[:, [A.NI_AUX, A.NI_MAT1, A.NI_MAT2]]):
+            return None
+        self.node_i[first:end] = new_i
+        self.node_f[first:end] = new_f
+        for k, leaf in zip(old_i[:, A.NI_LEAF][old_i[:, A.NI_LEAF] >= 0].tolist(), new_leaves):
+            self.leaves[k] = leaf
+        changed = list(range(first, end))
+        parents = self._parents()
+        p = parents.get(first, -1)
+        while p >= 0:  # ancestors: re-read the object's own box; synthetic wrappers take the union of their children
+            owner = owners.get(p)
+            if owner is not None:
+                box = [float(v) for v in owner.bbox]
+            else:
+                kids, j = [], p + 1
+                while j < self.node_i[p, A.NI_SKIP]:
+                    kids.append(self.node_f[j, A.NF_AABB:A.NF_AABB + 6])
+                    j = int(self.node_i[j, A.NI_SKIP])
+                kids = np.array(kids)
+                lo, hi = kids[:, 0::2].min(axis=0), kids[:, 1::2].max(axis=0)
+                box = [lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]]
+            if not np.array_equal(self.node_f[p, A.NF_AABB:A.NF_AABB + 6], box):
+                self.node_f[p, A.NF_AABB:A.NF_AABB + 6] = box
+                changed.append(p)
+            p = parents.get(p, -1)
+        return changed
+
+    def _parents(self):
+        """node -> parent node (cached): from the skip pointers of the pre-order table."""
+        cache = getattr(self, "_parent_cache", None)
+        if cache is None:
+            cache, open_ = {}, []
+            for i in range(self.n_nodes):
+                while open_ and self.node_i[open_[-1], A.NI_SKIP] <= i:
+                    open_.pop()
+                if open_:
+                    cache[i] = open_[-1]
+                if self.node_i[i, A.NI_GEOM] in (A.G_GROUP, A.G_GRID):
+                    open_.append(i)
+            self._parent_cache = cache
+        return cache
 
     # -- tree walk ---------------------------------------------------------------------------
     # Large groups get synthetic sub-groups over contiguous runs of children (a BVH in list order). The box of a
@@ -270,6 +362,9 @@ class FlatScene:
     def _emit(self, tree):
         """Append a (sub)tree in pre-order; `skip` = index of the first node after the subtree."""
         ni, nf, children = tree
+        comp = self._row_owner.get(id(ni))
+        if comp is not None:
+            self._node_of[id(comp)] = len(self._ni)
         self._ni.append(ni)
         self._nf.append(nf)
         for child in children:
@@ -360,6 +455,7 @@ class FlatScene:
             if len(comp.components) == 0:
                 return None  # nothing to hit (the reference would raise in merge_bboxs on first use)
             ni, nf = self._blank()
+            self._row_owner[id(ni)] = comp
             ni[A.NI_GEOM] = A.G_GROUP
             ni[A.NI_AABB] = 1
             nf[A.NF_AABB:A.NF_AABB + 6] = [float(v) for v in comp.bbox]
@@ -376,6 +472,7 @@ class FlatScene:
         if "Monitor" in names:
             raise FlattenError("a Monitor inside table.components is a pass-through that re-hits itself; unsupported")
         ni, nf = self._blank()
+        self._row_owner[id(ni)] = comp
         ni[A.NI_AABB] = 1 if in_group else 0
         ni[A.NI_LEAF] = len(self.leaves)
         self.leaves.append(comp)

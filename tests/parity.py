@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 RTOL = 1e-9
+Q_RTOL_FD = 2e-7   # Gaussian q behind a surface whose curvature the reference takes from a finite-difference stencil
 # Distances along a ray are compared relative to max(|t|, LENGTH_FLOOR): the reference takes a curved-surface hit from
 # scipy's brentq with xtol = 2e-12 (absolute), so its own t is only defined to 2e-12; RTOL * LENGTH_FLOOR is that.
 LENGTH_FLOOR = 2e-3
@@ -79,10 +80,13 @@ def q_rtol_for(flat):
     """Tolerance on the Gaussian q for a scene. After an ASphere, q depends on a radius of curvature that the
     reference takes from a finite-difference second derivative (surfaces.py:355-369, h = 1e-4 radius): one ulp in
     the local hit point or in f_asphere moves ROC by ~5e-9 relative (rounding noise / h^2), in the reference
-    itself. Scenes with such surfaces compare q to 1e-6; every other field and scene keeps the 1e-9 bar."""
+    itself: the curvature the REFERENCE computes is a smooth function of the hit point plus rounding noise of ~1e-8
+    relative that is resampled by any change of the hit point, however small. Scenes with such surfaces compare q to
+    2e-7 (SURVEY A.11 budgeted ~1e-7 per surface; observed 3e-8 at 4096 rays, 7e-8 at 3e6 rays through two lenses);
+    every other field and scene keeps the 1e-9 bar."""
     from optable_b200 import _abi as A
 
-    return 1e-6 if (flat.node_i[:, A.NI_ROCKIND] == A.ROC_ASPHERE_FD).any() else RTOL
+    return Q_RTOL_FD if (flat.node_i[:, A.NI_ROCKIND] == A.ROC_ASPHERE_FD).any() else RTOL
 
 
 def _without_roots(arrs, roots):

@@ -313,7 +313,7 @@ def test_device_monitor_analytics_match_reference_monitor_methods(name):
     bundle = RayBundle({k: arrs[k] for k in A.RAY_F64}, len(sc.rays))
     out = table.trace_bundle(bundle, sc.limit)
     checked = 0
-    q_tol = 1e-6 if name == "telescope_4f" else 1e-9   # waist distances after an ASphere: SURVEY A.11
+    q_tol = parity.Q_RTOL_FD * 5 if name in ("telescope_4f", "ripa2_simplified") else 1e-9   # Re(q) behind FD-curvature aspheres; the real part alone can be much smaller than |q|
     for m, mon in enumerate(table.monitors):
         pre = f"{name}__{m}__"
         if pre + "yList" not in z.files:
@@ -343,3 +343,40 @@ def test_device_monitor_analytics_match_reference_monitor_methods(name):
         assert st["mean_y"] == pytest.approx(z[pre + "yList"].mean(), rel=1e-9, abs=1e-12)
         checked += 1
     assert checked >= 1
+
+
+def test_gui_loop_refresh_update_nodes_and_graph_replay():
+    """f3 (optable/interact.py:455-457: one slider event = the scene with ONE component moved, traced again): the moved
+    component is re-read in place (FlatScene.refresh), its rows go to the device copy of the scene
+    (optb_scene_update_nodes) and the captured CUDA graph of the trace is replayed. Every replay must equal a trace
+    of a freshly flattened, freshly uploaded scene."""
+    import torch
+
+    from optable_b200.backend import Engine
+    from optable_b200.bundle import DeviceTrace, RayBundle
+    from optable_b200.flatten import FlatScene
+
+    engine = Engine.get(0)
+    sc = scenes.telescope_4f(ob, n_rays=0)
+    n = 50_000
+    rays = RayBundle.collimated_disc(n, radius=2.5).to_torch(device="cuda:0")
+    flat = FlatScene(sc.components, sc.monitors)
+    live = DeviceTrace(engine, flat, n, 2 * n + 64, record_hist=True)
+    live.capture(rays)
+    lens2 = sc.components[1]
+    for step in range(4):
+        lens2.TX(0.05).RotZ(2e-3)
+        changed = flat.refresh(lens2)
+        assert changed is not None and len(changed) == 3
+        live.scene.update_nodes(changed)
+        live.replay()
+        fresh = DeviceTrace(engine, FlatScene(sc.components, sc.monitors), n, 2 * n + 64, record_hist=True)
+        fresh.run(rays)
+        a, b = live.counters(), fresh.counters()
+        assert a[A.C_STATUS] == 0 and list(a[:5]) == list(b[:5]) and a[A.C_INTERACTIONS] > 3 * n
+        assert torch.equal(live.t["hist_yz"], fresh.t["hist_yz"]) and torch.equal(live.t["hist_y"], fresh.t["hist_y"])
+        nh = int(a[A.C_HITS])
+        for col in ("hit_py", "hit_t", "hit_q_im"):
+            assert torch.equal(torch.sort(live.t[col][:nh]).values, torch.sort(fresh.t[col][:nh]).values), col
+        fresh.close()
+    live.close()

@@ -40,7 +40,7 @@ def test_c2_4f_asphere_200k(engine):
 
     sc = scenes.telescope_4f(ob, n_rays=0)
     arrs = RayBundle.collimated_disc(200_000, start=12345).materialise()
-    got, errs = _both(engine, sc, arrs, q_rtol=1e-6)
+    got, errs = _both(engine, sc, arrs, q_rtol=parity.Q_RTOL_FD)
     assert int(got["counters"][1]) == 4 * 200_000
 
 

@@ -157,3 +157,40 @@ def test_callable_material_becomes_a_per_wavelength_table():
         tab = flat.aux[off:off + 2 * cnt].reshape(-1, 2)
         np.testing.assert_array_equal(tab[:, 0], wl)
         assert np.all(tab[:, 1] > 1.4) and np.all(np.diff(tab[:, 1]) < 0)   # normal dispersion of both laws
+
+
+def test_refresh_rewrites_a_moved_component_in_place():
+    """f3: FlatScene.refresh(component) = the rows a full re-flatten would produce, for a top-level leaf, a small group
+    and a leaf deep inside the 7,689-leaf ripa scene (where it also has to take well under 5 ms); changes that cannot
+    be expressed in place (a group with a synthetic box hierarchy, a new material) are refused with None."""
+    import time
+
+    sc = scenes.gaussian_beam(ob)
+    flat = FlatScene(sc.components, sc.monitors)
+    sc.components[0].TX(0.5).RotZ(0.1)
+    assert flat.refresh(sc.components[0]) == [0]
+    sc.components[4].TX(0.3)                                  # GlassSlab: a group of two faces
+    changed = flat.refresh(sc.components[4])
+    fresh = FlatScene(sc.components, sc.monitors)
+    assert changed == [4, 5, 6]
+    np.testing.assert_array_equal(flat.node_i, fresh.node_i)
+    np.testing.assert_array_equal(flat.node_f, fresh.node_f)
+    assert flat.leaves[int(flat.node_i[5, 9])] is sc.components[4].components[0]
+    # a change of material adds a table row: not expressible in place
+    sc.components[4].components[0]._n2 = ob.Material("other", n=1.7)
+    assert flat.refresh(sc.components[4]) is None
+
+    big = scenes.ripa(ob, n_rays=0)
+    flat = FlatScene(big.components, big.monitors)
+    fold = big.components[0].components[1]                    # a fold mirror inside the first ripa group
+    fold.RotY(1e-3)
+    flat.refresh(fold)                                        # (first call builds the parent table)
+    fold.RotY(1e-3)
+    t0 = time.perf_counter()
+    changed = flat.refresh(fold)
+    dt = time.perf_counter() - t0
+    fresh = FlatScene(big.components, big.monitors)
+    np.testing.assert_array_equal(flat.node_i, fresh.node_i)
+    np.testing.assert_array_equal(flat.node_f, fresh.node_f)
+    assert changed and len(changed) <= 3 and dt < 5e-3, (changed, dt)
+    assert flat.refresh(big.components[0].components[3]) is None   # an MMA: box hierarchy + lattice descriptor
