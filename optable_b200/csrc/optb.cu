@@ -31,12 +31,6 @@ namespace {
 #ifndef OPTB_MIN_BLOCKS
 #define OPTB_MIN_BLOCKS 4
 #endif
-#ifndef OPTB_UNIFORM_WALK
-#define OPTB_UNIFORM_WALK 1  // param-scene kernels: warp-uniform node loop (closest_hit_uniform)
-#endif
-#ifndef OPTB_PARAM_SCENE
-#define OPTB_PARAM_SCENE 1   // 0: small scenes are staged in shared memory (TMA) like medium ones (A/B switch)
-#endif
 #ifndef OPTB_GRID_WALK
 #define OPTB_GRID_WALK 1   // 0: ignore the lattice descriptors (A/B switch; OPTB_G_GRID nodes are then plain groups)
 #endif
@@ -72,12 +66,6 @@ struct Header {  // first bytes of the workspace
 
 struct SceneOff { uint32_t trav, nf, ni, matk, matf, mon, aux; };
 
-// Small scenes ride in the kernel parameters themselves (constant bank): a table entry read at a warp-uniform index is
-// then an operand fetched through the constant cache / uniform datapath instead of a shared-memory load into a
-// register of every thread, and branches on it are uniform branches.
-constexpr uint32_t kParamSceneBytes = 6144;
-struct __align__(16) ParamScene { unsigned char bytes[kParamSceneBytes]; };
-
 struct TraceArgs {
   const unsigned char* blob; uint32_t blob_bytes; SceneOff off; int n_nodes, n_mons;
   // input wavefront: either the caller's rays (gen0) or the workspace wavefront
@@ -100,7 +88,6 @@ struct TraceArgs {
   uint32_t root_base;  // global index of ray 0 of this launch (chunked host traces)
   int has_boxes;       // some node carries a lab-box test
 };
-struct TraceArgsP { TraceArgs a; ParamScene ps; };  // parameters of the param-scene kernel variants
 
 OPTB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -441,64 +428,18 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   if (BOXES) atomicAdd(cnt + 2 * kBlock, n_box);
 }
 
-// Closest hit for scenes whose tables live in the kernel parameters (trace_kernel_p): the same decisions as closest_hit,
-// with the node loop made warp-uniform. Every lane visits every node in pre-order; a failed box test masks the lane
-// until the end of that subtree instead of making it jump. The loop index is then the same in all lanes, table entries
-// are fetched through the uniform datapath / as constant operands, and the branches on a node's kind are uniform.
-// (Scenes of this size have at most a few dozen nodes: visiting a masked node costs a predicate, not a test.)
-template <int BOXES, bool ASPH>
-OPTB_DEV void closest_hit_uniform(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
-                                  double& best_t, int& best_node, unsigned int* cnt) {
-  HitSearch<ASPH, false> hs{a, sv, ray, solo, INFINITY, -1, cnt};
-  const bool alive = (ray.flags & OPTB_RF_ALIVE) != 0;  // optical_component.py:349-350: a dead ray hits nothing
-  const BoxRay br(ray.ox, ray.oy, ray.oz, BOXES ? ray.dx : 1.0, BOXES ? ray.dy : 1.0, BOXES ? ray.dz : 1.0);
-  unsigned int n_box = 0;
-  int skip_until = 0;          // this lane skips nodes below this index (a box it missed)
-  unsigned int asph_mask = 0;  // aspheres this lane still has to test (bit = position among the scene's aspheres)
-  const int n = sv.n_nodes;
-  int n_asph = 0;
-  for (int i = 0; i < n; i++) {
-    const double* tv = sv.trav + i * 8;
-    const int2 gs = *reinterpret_cast<const int2*>(tv + 6);  // {geometry kind, skip}: uniform
-    bool active = alive && i >= skip_until;
-    if (BOXES && *reinterpret_cast<const int*>(tv + 7)) {
-      if (active) {
-        n_box++;
-        if (!slab_hit(br, tv)) { skip_until = gs.y; active = false; }
-      }
-    }
-    const int g = gs.x;
-    if (g == OPTB_G_GROUP || g == OPTB_G_GRID) continue;
-    if (ASPH && g == OPTB_G_ASPHERE) {  // parked: tested last, against the closest cheap hit (see closest_hit)
-      if (active && n_asph < 32) asph_mask |= 1u << n_asph;
-      else if (active) hs.test_leaf(i, sv.ni + i * OPTB_NI_STRIDE, sv.nf + i * OPTB_NF_STRIDE);
-      n_asph++;
-      continue;
-    }
-    if (active) hs.test_leaf(i, sv.ni + i * OPTB_NI_STRIDE, sv.nf + i * OPTB_NF_STRIDE);
-  }
-  if (ASPH) {
-    int k = 0;
-    for (int i = 0; i < n && k < 32; i++) {
-      if (reinterpret_cast<const int2*>(sv.trav + i * 8 + 6)->x != OPTB_G_ASPHERE) continue;
-      if ((asph_mask >> k) & 1u) hs.test_leaf(i, sv.ni + i * OPTB_NI_STRIDE, sv.nf + i * OPTB_NF_STRIDE);
-      k++;
-    }
-  }
-  best_t = hs.best_t; best_node = hs.best_node;
-  if (BOXES) atomicAdd(cnt + 2 * kBlock, n_box);
-}
-
 // SPLIT = some interaction of the scene can emit two rays (or the caller bounded the in-register chain): the
 // wavefront machinery (child slots, per-root generation ranks) is compiled in. Scenes that cannot split run the
 // whole life of a ray in registers with none of it.
 // FLAG = diagnostics variant: the ambiguity mask of SURVEY A.9 is evaluated at every pop (optb_flags.cuh).
 // BRENT = params.reference_roots: curved-surface roots from the reference's own brentq iteration (brentq_dev) instead
 // of the closed-form / Newton root.
-// SMEM: where the scene tables are read from: 0 = global memory (L1/L2), 1 = shared memory (staged by TMA),
-//       2 = the kernel parameters (constant bank; `pscene`).
-template <int SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = false, bool BRENT = false>
-OPTB_DEV void trace_body(const TraceArgs& a, const unsigned char* pscene) {
+template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = false, bool BRENT = false>
+// Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
+// spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
+// whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
+__global__ void __launch_bounds__(kBlock, (SMEM || ASPH || SERIAL) ? OPTB_MIN_BLOCKS : OPTB_MIN_BLOCKS + 1)
+trace_kernel(const __grid_constant__ TraceArgs a) {
   constexpr int MAXCH = (SPLIT || SERIAL) ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -513,8 +454,8 @@ OPTB_DEV void trace_body(const TraceArgs& a, const unsigned char* pscene) {
   s_icn[0][threadIdx.x] = -1.0; s_icm[0][threadIdx.x] = -1; s_icm[1][threadIdx.x] = -1;
   const IndexCache ic{&s_icn[0][threadIdx.x], &s_icn[1][threadIdx.x], &s_icn[2][threadIdx.x], &s_icm[0][threadIdx.x],
                       &s_icm[1][threadIdx.x]};
-  const unsigned char* base = SMEM == 2 ? pscene : a.blob;
-  if constexpr (SMEM == 1) {
+  const unsigned char* base = a.blob;
+  if constexpr (SMEM) {
     // Stage the whole scene blob with TMA bulk copies; completion is signalled on the mbarrier.
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
     __syncthreads();
@@ -539,7 +480,7 @@ OPTB_DEV void trace_body(const TraceArgs& a, const unsigned char* pscene) {
   sv.status = &a.counters[OPTB_C_STATUS];
 
   const int per = OPTB_HIST_BINS * (OPTB_HIST_BINS + 1);
-  unsigned int* s_hist = (unsigned int*)(smem_raw + (SMEM == 1 ? ((a.blob_bytes + 15u) & ~15u) : 0u));
+  unsigned int* s_hist = (unsigned int*)(smem_raw + (SMEM ? ((a.blob_bytes + 15u) & ~15u) : 0u));
   if (a.hist_smem) {
     for (int k = threadIdx.x; k < a.n_mons * per; k += blockDim.x) s_hist[k] = 0u;
     __syncthreads();
@@ -627,8 +568,7 @@ OPTB_DEV void trace_body(const TraceArgs& a, const unsigned char* pscene) {
         volatile double* pk = &s_park[0][threadIdx.x];
         pk[0 * kBlock] = ray.I; pk[1 * kBlock] = ray.wl; pk[2 * kBlock] = ray.qre;
         pk[3 * kBlock] = ray.qim; pk[4 * kBlock] = ray.pl; pk[5 * kBlock] = ray.n;
-        if constexpr (SMEM == 2 && OPTB_UNIFORM_WALK) closest_hit_uniform<BOXES, ASPH>(a, sv, ray, solo, t, node, my_cnt);
-        else closest_hit<BOXES, ASPH, BRENT>(a, sv, ray, solo, t, node, my_cnt);
+        closest_hit<BOXES, ASPH, BRENT>(a, sv, ray, solo, t, node, my_cnt);
         ray.I = pk[0 * kBlock]; ray.wl = pk[1 * kBlock]; ray.qre = pk[2 * kBlock];
         ray.qim = pk[3 * kBlock]; ray.pl = pk[4 * kBlock]; ray.n = pk[5 * kBlock];
       }
@@ -701,21 +641,6 @@ OPTB_DEV void trace_body(const TraceArgs& a, const unsigned char* pscene) {
                      (unsigned long long)cnt);
     }
   }
-}
-
-// Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
-// spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
-// whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
-template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = false, bool BRENT = false>
-__global__ void __launch_bounds__(kBlock, (SMEM || ASPH || SERIAL) ? OPTB_MIN_BLOCKS : OPTB_MIN_BLOCKS + 1)
-trace_kernel(const __grid_constant__ TraceArgs a) {
-  trace_body<SMEM ? 1 : 0, SERIAL, BOXES, ASPH, SPLIT, FLAG, BRENT>(a, nullptr);
-}
-// the same loop with the scene tables in the kernel parameters (scenes up to kParamSceneBytes, parallel path)
-template <int BOXES, bool ASPH, bool SPLIT>
-__global__ void __launch_bounds__(kBlock, OPTB_MIN_BLOCKS)
-trace_kernel_p(const __grid_constant__ TraceArgsP p) {
-  trace_body<2, false, BOXES, ASPH, SPLIT>(p.a, p.ps.bytes);
 }
 
 // ---- ordered compaction of the sparse children into the next wavefront --------------------------------
@@ -906,7 +831,6 @@ struct optb_ctx {
   int64_t live_per_ray_hint;
   // NCCL communicator for optb_monitor_merge (library loaded at run time)
   void* nccl_lib; void* nccl_comm; int comm_rank, comm_size; long long* d_merge;  // d_merge: device scratch of the merge
-  TraceArgsP param_args;  // staging of the (large) parameter block of trace_kernel_p
 };
 
 struct optb_scene {
@@ -917,7 +841,6 @@ struct optb_scene {
   // recorded on the stream of every trace that reads the blob: releasing the scene waits for this event only,
   // not for the whole device (other streams, NCCL and unrelated kernels keep running)
   cudaEvent_t last_use; bool used;
-  ParamScene* host_blob;  // host copy of a blob that fits the kernel parameters (else null)
 };
 
 static int fail(optb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -1109,10 +1032,6 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
     if (e != cudaSuccess) { delete s; return fail(ctx, -10, "cudaMalloc(scene)", e); }
   }
   e = cudaMemcpy(s->d_blob, host.data(), o, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && o <= kParamSceneBytes) {
-    s->host_blob = new (std::nothrow) ParamScene();
-    if (s->host_blob) { memset(s->host_blob, 0, sizeof(ParamScene)); memcpy(s->host_blob->bytes, host.data(), o); }
-  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->last_use, cudaEventDisableTiming);
   if (e != cudaSuccess) { cudaFree(s->d_blob); delete s; return fail(ctx, -10, "cudaMemcpy(scene)", e); }
   *out = s;
@@ -1135,11 +1054,6 @@ extern "C" int optb_scene_update_nodes(optb_ctx* ctx, optb_scene* s, const optb_
     CK(cudaMemcpyAsync(s->d_blob + s->off.nf + (size_t)i * OPTB_NF_STRIDE * 8, nf, OPTB_NF_STRIDE * 8, cudaMemcpyHostToDevice, st), "update node_f");
     CK(cudaMemcpyAsync(s->d_blob + s->off.ni + (size_t)i * OPTB_NI_STRIDE * 4, ni, OPTB_NI_STRIDE * 4, cudaMemcpyHostToDevice, st), "update node_i");
     CK(cudaMemcpyAsync(s->d_blob + s->off.trav + (size_t)i * 64, nf + OPTB_NF_AABB, 48, cudaMemcpyHostToDevice, st), "update box");
-    if (s->host_blob) {
-      memcpy(s->host_blob->bytes + s->off.nf + (size_t)i * OPTB_NF_STRIDE * 8, nf, OPTB_NF_STRIDE * 8);
-      memcpy(s->host_blob->bytes + s->off.ni + (size_t)i * OPTB_NI_STRIDE * 4, ni, OPTB_NI_STRIDE * 4);
-      memcpy(s->host_blob->bytes + s->off.trav + (size_t)i * 64, nf + OPTB_NF_AABB, 48);
-    }
   }
   // scene-wide properties that pick the kernel variant follow the new rows
   int mc = 0, boxes = 0, asph = 0;
@@ -1176,7 +1090,6 @@ extern "C" int optb_scene_destroy(optb_ctx* ctx, optb_scene* s) {
     }
   }
   if (s->last_use) cudaEventDestroy(s->last_use);
-  delete s->host_blob;
   delete s;
   return 0;
 }
@@ -1375,22 +1288,8 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
     if (prm->flag_ambiguity) return fail(ctx, -7, "reference_roots and flag_ambiguity are separate diagnostics modes");
     kern = brent_table[serial ? 1 : 0][scene->in_smem ? 1 : 0];
   }
-  // scenes that fit the kernel parameters (and are read-only during the call: host copy kept at upload)
-  using KernP = void (*)(const TraceArgsP);
-#define OPTB_KP(B) {{trace_kernel_p<B, false, false>, trace_kernel_p<B, false, true>}, {trace_kernel_p<B, true, false>, trace_kernel_p<B, true, true>}}
-  static const KernP ptable[2][2][2] = {OPTB_KP(0), OPTB_KP(1)};
-#undef OPTB_KP
-  KernP kernp = nullptr;
-  if (OPTB_PARAM_SCENE && !serial && !prm->flag_ambiguity && !prm->reference_roots && boxmode < 2 && scene->host_blob &&
-      scene->blob_bytes <= kParamSceneBytes)
-    kernp = ptable[boxmode][scene->has_asph ? 1 : 0][split ? 1 : 0];
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
   int occ = 1;
-  if (kernp) {  // (tables in the parameters: dynamic shared memory only holds the histograms)
-    smem = a.hist_smem ? (uint32_t)((size_t)scene->n_mons * OPTB_HIST_BINS * (OPTB_HIST_BINS + 1) * 4) : 0;
-    CK(cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 1024)), "smem attr");
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernp, kBlock, smem), "occupancy");
-  } else
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem), "occupancy");
   if (occ < 1) occ = 1;
   const int full_grid = ctx->sm_count * occ;
@@ -1451,17 +1350,8 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
       int grid = (int)std::min<long long>(full_grid, want);
       a.n_in = bound;
       a.n_in_dev = unseen ? &hdr->n_next : nullptr;
-      if (kernp) {
-        // (the parameter block is copied by the launch: later changes of `a` or of the host blob do not reach it)
-        TraceArgsP* pa = &ctx->param_args;
-        pa->a = a;
-        memcpy(&pa->ps, scene->host_blob, sizeof(ParamScene));
-        void* kargs[] = {(void*)pa};
-        CK(cudaLaunchKernel((const void*)kernp, dim3(grid), dim3(kBlock), kargs, smem, st), "launch trace_kernel_p");
-      } else {
-        void* kargs[] = {(void*)&a};
-        CK(cudaLaunchKernel((const void*)kern, dim3(grid), dim3(kBlock), kargs, smem, st), "launch trace_kernel");
-      }
+      void* kargs[] = {(void*)&a};
+      CK(cudaLaunchKernel((const void*)kern, dim3(grid), dim3(kBlock), kargs, smem, st), "launch trace_kernel");
       launches++; gens++;
       if (!split) break;
       int ntiles = (int)((bound + kTile - 1) / kTile);
