@@ -34,7 +34,14 @@ namespace {
 #ifndef OPTB_GRID_WALK
 #define OPTB_GRID_WALK 1   // 0: ignore the lattice descriptors (A/B switch; OPTB_G_GRID nodes are then plain groups)
 #endif
-constexpr int kBlock = 128;
+#ifndef OPTB_BLOCK
+#define OPTB_BLOCK 128
+#endif
+#ifndef OPTB_PHASE_SYNC
+#define OPTB_PHASE_SYNC 1   // 0: no per-pop CTA barrier in any variant (A/B switch)
+#endif
+constexpr int kBlock = OPTB_BLOCK;
+constexpr int kResident(int ctas_of_128) { return ctas_of_128 * 128 / kBlock > 0 ? ctas_of_128 * 128 / kBlock : 1; }
 constexpr int kTile = 2048;  // children-scan tile (entries per block)
 constexpr int kScanBlock = 256;
 constexpr int kRayF64 = 13;
@@ -438,7 +445,7 @@ template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = 
 // Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
 // spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
 // whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
-__global__ void __launch_bounds__(kBlock, (SMEM || ASPH || SERIAL) ? OPTB_MIN_BLOCKS : OPTB_MIN_BLOCKS + 1)
+__global__ void __launch_bounds__(kBlock, kResident((SMEM || ASPH || SERIAL) ? OPTB_MIN_BLOCKS : OPTB_MIN_BLOCKS + 1))
 trace_kernel(const __grid_constant__ TraceArgs a) {
   constexpr int MAXCH = (SPLIT || SERIAL) ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -495,11 +502,23 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
     if (lane == 0) chunk = atomicAdd(&a.hdr->work_ctr, 1u);
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     long long i = (long long)chunk * 32 + lane;
-    if ((long long)chunk * 32 >= n_in) break;
-    if (i >= n_in) continue;
+    // PHASE: the warps of a CTA start every pop together (one barrier per pop). The kernel's hot code (35-55 KB) is
+    // larger than the 32 KB instruction cache; rays of one launch follow similar paths, so warps that start a pop
+    // together run the same stretch of code at the same time and share the cache instead of thrashing it (ncu on the
+    // ripa scene: 4.8 issue slots lost to instruction fetch per instruction issued). Used where it measured faster
+    // (B200, r2n): scenes with a box walk and no aspheres -- lens groups of spheres (c3 -5 %), large arrays
+    // (ripa -6 %); not for bare mirror scenes, whose pops are too short to pay for a barrier (c4 +17 %), nor for
+    // asphere scenes (c2 +-0). A warp that ran out of rays keeps meeting the barrier until the whole CTA is done.
+    constexpr bool PHASE = OPTB_PHASE_SYNC && !SERIAL && !FLAG && BOXES != 0 && !ASPH;
+    const bool has = i < n_in;
+    if (PHASE) { if (!__syncthreads_or(has ? 1 : 0)) break; }
+    else {
+      if ((long long)chunk * 32 >= n_in) break;
+      if (!has) continue;
+    }
     // Wavefront entries are stored in reference (BFS) order, which the pop numbering needs, but processed in the
     // order of their coherence key: rays that left the same surface the same way sit in the same warp.
-    if (SPLIT && !SERIAL && a.perm) i = a.perm[i];
+    if (SPLIT && !SERIAL && a.perm && has) i = a.perm[i];
 
     if constexpr (SERIAL) {
       // Work item = one Ray._id family. Its initial rays are traced one after another in input order, each
@@ -552,8 +571,8 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
       continue;
     }
 
-    Ray ray; bool solo; uint32_t gcount, pop_base0;
-    load_ray(a, i, ray, solo, gcount, pop_base0);
+    Ray ray; bool solo = true; uint32_t gcount = 1, pop_base0 = 0;
+    if (has) load_ray(a, i, ray, solo, gcount, pop_base0);
     if (!SPLIT) solo = true;
     const uint32_t pop_base_next = (!SPLIT || a.gen0) ? 0u : (pop_base0 + gcount);
     int nch = 0;
@@ -561,8 +580,9 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
     int hit_leaf = 0;
     Children<MAXCH> ch;
     ch.n = 0;
-    while (true) {
-      if ((long long)ray.pop >= a.max_trace) { c_drop++; nch = 0; break; }  // queued but never popped
+    // one pop of this lane's ray; true = its only child carries on in registers (chain)
+    auto pop_step = [&]() -> bool {
+      if ((long long)ray.pop >= a.max_trace) { c_drop++; nch = 0; return false; }  // queued but never popped
       double t; int node;
       {
         volatile double* pk = &s_park[0][threadIdx.x];
@@ -584,7 +604,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
       const double* nf = sv.nf + (hit ? node : 0) * OPTB_NF_STRIDE;
       emit_segment(a, sv, ray, hit ? t : ray.len, hit ? (ray.flags & ~OPTB_RF_ALIVE) : ray.flags,
                    hit ? ni[OPTB_NI_LEAF] : -1, s_hist, c_hits);
-      if (!hit) { nch = 0; break; }
+      if (!hit) { nch = 0; return false; }
       c_inter++;
       hit_leaf = ni[OPTB_NI_LEAF];
       double ox, oy, oz, dx, dy, dz;
@@ -597,12 +617,20 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
         ray.dx = ch.dx[0]; ray.dy = ch.dy[0]; ray.dz = ch.dz[0];
         ray.I = ch.I[0]; ray.qre = ch.qre[0]; ray.qim = ch.qim[0]; ray.pl = ch.pl; ray.n = ch.nmed[0];
         ray.pop++; chained++;
-        continue;
+        return true;
       }
-      break;
+      return false;
+    };
+    if constexpr (PHASE) {
+      bool active = has;
+      while (__syncthreads_or(active ? 1 : 0)) {
+        if (active) active = pop_step();
+      }
+    } else {
+      while (pop_step()) {}
     }
     if constexpr (SPLIT) {
-      if (a.nchild) {
+      if (a.nchild && has) {
         a.nchild[i] = (uint8_t)nch;
         uint32_t pb = solo ? ray.pop + 1u : pop_base_next;
         if (nch > 0) store_child(a.c, 2 * i, ray, ch.ox, ch.oy, ch.oz, ch.pl, ch.dx[0], ch.dy[0], ch.dz[0], ch.I[0],
@@ -1408,7 +1436,10 @@ static int trace_host_once(optb_ctx* ctx, const optb_scene* scene, const optb_ra
 static int trace_host_pipelined(optb_ctx* ctx, const optb_scene* scene, const optb_rays* rays, const optb_params* prm,
                                 optb_result* out) {
   cudaSetDevice(ctx->device);
-  constexpr int64_t kChunk = 1 << 20;
+#ifndef OPTB_HOST_CHUNK
+#define OPTB_HOST_CHUNK (1 << 20)
+#endif
+  constexpr int64_t kChunk = OPTB_HOST_CHUNK;
   const int64_t n = rays->n;
   const int nch = (int)((n + kChunk - 1) / kChunk);
   const int64_t segcap = prm->record_segments ? out->seg_capacity : 0, hitcap = prm->record_hits ? out->hit_capacity : 0;
