@@ -37,6 +37,13 @@ namespace {
 #ifndef OPTB_BLOCK
 #define OPTB_BLOCK 128
 #endif
+#ifndef OPTB_VOTE_SMEM
+#define OPTB_VOTE_SMEM 0   // 1: the walk of shared-memory scenes also re-converges its lanes with a vote before each leaf test
+#endif
+#ifndef OPTB_PARK_ALWAYS
+#define OPTB_PARK_ALWAYS 0   // 1: every variant parks the radiometric ray state in shared memory during the hit search
+                             // (0: only asphere / lattice variants; measured r2u: c4 115.0 -> 110.8 ms, c3 8.00 -> 7.81)
+#endif
 #ifndef OPTB_PHASE_SYNC
 #define OPTB_PHASE_SYNC 1   // 0: no per-pop CTA barrier in any variant (A/B switch)
 #endif
@@ -200,7 +207,7 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
     }
   }
   for (int m = 0; m < sv.n_mons; m++) {
-    const double* mf = sv.mon + m * OPTB_MON_STRIDE;
+    const double* mf = sv.mon + m * kMonBlobStride;
     // Monitor.record (monitor.py:183-193) = to-local + planar hit with t <= length, in stages like intersect_planar:
     // the x row of Tinv decides "in front, not parallel" and (orthonormal frame) gives t; most segments end here
     const double* c = mf + OPTB_MON_ORIGIN;
@@ -230,8 +237,8 @@ OPTB_COLD void emit_segment(const TraceArgs& a, const SceneView& sv, const Ray& 
     if (a.rec_hist) {
       double y = dot3(Px, Py, Pz, mf[OPTB_MON_TY], mf[OPTB_MON_TY + 1], mf[OPTB_MON_TY + 2]);
       double z = dot3(Px, Py, Pz, mf[OPTB_MON_TZ], mf[OPTB_MON_TZ + 1], mf[OPTB_MON_TZ + 2]);
-      int by = hist_bin(y, -mf[OPTB_MON_HW], mf[OPTB_MON_HW]);
-      int bz = hist_bin(z, -mf[OPTB_MON_HH], mf[OPTB_MON_HH]);
+      int by = hist_bin(y, -mf[OPTB_MON_HW], mf[OPTB_MON_HW], mf[OPTB_MON_STRIDE], mf[OPTB_MON_STRIDE + 1]);
+      int bz = hist_bin(z, -mf[OPTB_MON_HH], mf[OPTB_MON_HH], mf[OPTB_MON_STRIDE + 2], mf[OPTB_MON_STRIDE + 3]);
       const int per = OPTB_HIST_BINS * (OPTB_HIST_BINS + 1);
       if (by >= 0) {
         if (a.hist_smem) {
@@ -346,12 +353,23 @@ OPTB_DEV bool grid_window(const double* __restrict__ gd, const Ray& r, int& i0, 
 //        2 = the same walk, and groups whose children form a regular lattice (OPTB_G_GRID: MMA / MLA / DMD arrays)
 //            hand the walk the few children inside the ray's lattice window instead of a descent through their
 //            box hierarchy; each candidate still has to pass the reference's own test of its own box.
-template <int BOXES, bool ASPH, bool BRENT = false>
+template <int BOXES, bool ASPH, bool BRENT = false, bool VOTE = true>
 OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ray, bool solo,
                           double& best_t, int& best_node, unsigned int* cnt) {
   best_t = INFINITY; best_node = -1;
   const bool no_work = !(ray.flags & OPTB_RF_ALIVE);  // optical_component.py:349-350: a dead ray hits nothing
   HitSearch<ASPH, BRENT> hs{a, sv, ray, solo, INFINITY, -1, cnt};
+  if constexpr (BOXES == 0 && !ASPH) {
+    // No node carries a box test, so there is no group (groups always do): every node is a top-level leaf, and without
+    // aspheres nothing is parked. The walk is a plain loop (c4: 687 -> ~600 warp instructions per pop).
+    if (!no_work) {
+      const int n = sv.n_nodes;
+#pragma unroll 1
+      for (int i = 0; i < n; i++) hs.test_leaf(i, sv.ni + i * OPTB_NI_STRIDE, sv.nf + i * OPTB_NF_STRIDE);
+    }
+    best_t = hs.best_t; best_node = hs.best_node;
+    return;
+  }
   unsigned int n_box = 0;
   constexpr int kPark = 4;
   int parked[kPark];
@@ -371,7 +389,8 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   const unsigned group = __activemask();
   bool searching = !no_work;
   // (scenes without box tests yield a leaf per walk step: all lanes are in lock-step anyway, no vote needed)
-  while (BOXES ? __any_sync(group, searching) : searching) {
+  // VOTE = false (scenes staged in shared memory: a few dozen nodes, mostly coherent bundles): no vote either
+  while ((BOXES && VOTE) ? __any_sync(group, searching) : searching) {
     int leaf = -1;
     if (searching) {
       while (true) {
@@ -584,13 +603,15 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
     auto pop_step = [&]() -> bool {
       if ((long long)ray.pop >= a.max_trace) { c_drop++; nch = 0; return false; }  // queued but never popped
       double t; int node;
-      {
+      if constexpr (OPTB_PARK_ALWAYS || ASPH || BOXES == 2) {
         volatile double* pk = &s_park[0][threadIdx.x];
         pk[0 * kBlock] = ray.I; pk[1 * kBlock] = ray.wl; pk[2 * kBlock] = ray.qre;
         pk[3 * kBlock] = ray.qim; pk[4 * kBlock] = ray.pl; pk[5 * kBlock] = ray.n;
-        closest_hit<BOXES, ASPH, BRENT>(a, sv, ray, solo, t, node, my_cnt);
+        closest_hit<BOXES, ASPH, BRENT, OPTB_VOTE_SMEM || SMEM != 1>(a, sv, ray, solo, t, node, my_cnt);
         ray.I = pk[0 * kBlock]; ray.wl = pk[1 * kBlock]; ray.qre = pk[2 * kBlock];
         ray.qim = pk[3 * kBlock]; ray.pl = pk[4 * kBlock]; ray.n = pk[5 * kBlock];
+      } else {
+        closest_hit<BOXES, ASPH, BRENT, OPTB_VOTE_SMEM || SMEM != 1>(a, sv, ray, solo, t, node, my_cnt);
       }
       c_pops++;
       if constexpr (FLAG) {
@@ -930,6 +951,15 @@ extern "C" int optb_ctx_destroy(optb_ctx* ctx) {
 
 extern "C" const char* optb_last_error(const optb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
+// Device-side extras of an asphere row: k1 of the sign / Newton functor (AsphF) in the FOCAL slot, which a refractive
+// leaf does not use. Same expressions, same IEEE operations as the device used to evaluate per test.
+static void asphere_constants(double* nf, const int32_t* ni) {
+  if (ni[OPTB_NI_GEOM] != OPTB_G_ASPHERE) return;
+  const double* c = nf + OPTB_NF_P + 1;
+  if (ni[OPTB_NI_AUX] == OPTB_ASPH_PARAMETRIC) nf[OPTB_NF_FOCAL] = (1.0 + c[1]) / (c[0] * c[0]);
+  else nf[OPTB_NF_FOCAL] = (c[1] + 1.0) / ((c[1] - 1.0) * c[0] * c[0]);
+}
+
 extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_scene** out) {
   if (!ctx || !d || !out) return -1;
   if (d->abi_version != OPTB_ABI_VERSION) return fail(ctx, -4, "scene ABI version mismatch");
@@ -987,7 +1017,7 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   s->n_caps = d->n_capslots; s->n_aux = d->n_aux;
   size_t b_nf = (size_t)d->n_nodes * OPTB_NF_STRIDE * 8, b_ni = (size_t)d->n_nodes * OPTB_NI_STRIDE * 4;
   size_t b_mk = (size_t)d->n_materials * 4, b_mf = (size_t)d->n_materials * OPTB_MF_STRIDE * 8;
-  size_t b_mon = (size_t)std::max(d->n_monitors, 1) * OPTB_MON_STRIDE * 8, b_aux = (size_t)std::max<long long>(d->n_aux, 1) * 8;
+  size_t b_mon = (size_t)std::max(d->n_monitors, 1) * kMonBlobStride * 8, b_aux = (size_t)std::max<long long>(d->n_aux, 1) * 8;
   size_t o = 0;
   const size_t b_trav = (size_t)std::max(d->n_nodes, 1) * 64;
   s->off.trav = (uint32_t)o; o = align_up(o + b_trav, 16);
@@ -1021,7 +1051,15 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
   }
   memcpy(host.data() + s->off.matk, d->mat_kind, b_mk);
   memcpy(host.data() + s->off.matf, d->mat_f, b_mf);
-  if (d->n_monitors) memcpy(host.data() + s->off.mon, d->mon_f, (size_t)d->n_monitors * OPTB_MON_STRIDE * 8);
+  for (int m = 0; m < d->n_monitors; m++) {  // ABI record + the histogram constants derived from it (kMonBlobStride)
+    double* mf = (double*)(host.data() + s->off.mon) + (size_t)m * kMonBlobStride;
+    memcpy(mf, d->mon_f + (size_t)m * OPTB_MON_STRIDE, OPTB_MON_STRIDE * 8);
+    const double w = mf[OPTB_MON_HW] - (-mf[OPTB_MON_HW]), h = mf[OPTB_MON_HH] - (-mf[OPTB_MON_HH]);  // hi - lo as hist_bin forms it
+    mf[OPTB_MON_STRIDE] = OPTB_HIST_BINS / w; mf[OPTB_MON_STRIDE + 1] = w / OPTB_HIST_BINS;
+    mf[OPTB_MON_STRIDE + 2] = OPTB_HIST_BINS / h; mf[OPTB_MON_STRIDE + 3] = h / OPTB_HIST_BINS;
+  }
+  for (int i = 0; i < d->n_nodes; i++) asphere_constants((double*)(host.data() + s->off.nf) + (size_t)i * OPTB_NF_STRIDE,
+                                                         d->node_i + (size_t)i * OPTB_NI_STRIDE);
   if (d->n_aux) memcpy(host.data() + s->off.aux, d->aux, (size_t)d->n_aux * 8);
   // most children one interaction can emit (decides whether the wavefront machinery is needed)
   int mc = 0;
@@ -1079,7 +1117,11 @@ extern "C" int optb_scene_update_nodes(optb_ctx* ctx, optb_scene* s, const optb_
     if (i < 0 || i >= d->n_nodes) return fail(ctx, -5, "optb_scene_update_nodes: node index out of range");
     const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
     const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
-    CK(cudaMemcpyAsync(s->d_blob + s->off.nf + (size_t)i * OPTB_NF_STRIDE * 8, nf, OPTB_NF_STRIDE * 8, cudaMemcpyHostToDevice, st), "update node_f");
+    double row[OPTB_NF_STRIDE];
+    memcpy(row, nf, sizeof row);
+    asphere_constants(row, ni);
+    // (pageable source: the call returns once `row` has been copied to the driver's staging memory)
+    CK(cudaMemcpyAsync(s->d_blob + s->off.nf + (size_t)i * OPTB_NF_STRIDE * 8, row, OPTB_NF_STRIDE * 8, cudaMemcpyHostToDevice, st), "update node_f");
     CK(cudaMemcpyAsync(s->d_blob + s->off.ni + (size_t)i * OPTB_NI_STRIDE * 4, ni, OPTB_NI_STRIDE * 4, cudaMemcpyHostToDevice, st), "update node_i");
     CK(cudaMemcpyAsync(s->d_blob + s->off.trav + (size_t)i * 64, nf + OPTB_NF_AABB, 48, cudaMemcpyHostToDevice, st), "update box");
   }

@@ -28,6 +28,10 @@
 
 namespace optb {
 
+// Device-side monitor record = the ABI record (OPTB_MON_STRIDE doubles) + per-monitor constants the upload derives from
+// it: [24] nb / w, [25] w / nb, [26] nb / h, [27] h / nb (np.histogram's norm and step for the y and z binning).
+constexpr int kMonBlobStride = OPTB_MON_STRIDE + 4;
+
 struct Ray {
   double ox, oy, oz, dx, dy, dz;
   double I, wl, qre, qim, pl, n, len;
@@ -223,13 +227,14 @@ struct AsphF {
   int form;
   double k1, R, sgn, a4, a6, a8;  // parametric: k1 = (1+kappa)/R^2 ; exact: k1 = (n+1)/((n-1) EFL^2), R = EFL/(n+1)
   double ox, oy, oz, dx, dy, dz;
-  OPTB_DEV AsphF(int form_, const double* __restrict__ c, double ox_, double oy_, double oz_, double dx_, double dy_, double dz_)
+  OPTB_DEV AsphF(int form_, const double* __restrict__ c, double k1_, double ox_, double oy_, double oz_, double dx_, double dy_, double dz_)
       : form(form_), ox(ox_), oy(oy_), oz(oz_), dx(dx_), dy(dy_), dz(dz_) {
+    k1 = k1_;  // precomputed by the upload with the expressions below (one division less per asphere test)
     if (form == OPTB_ASPH_PARAMETRIC) {
-      R = c[0]; k1 = (1.0 + c[1]) / (R * R); a4 = c[2]; a6 = c[3]; a8 = c[4];
+      R = c[0]; /* k1 = (1.0 + c[1]) / (R * R) */ a4 = c[2]; a6 = c[3]; a8 = c[4];
       sgn = R < 0 ? -1.0 : 1.0;
     } else {
-      k1 = (c[1] + 1.0) / ((c[1] - 1.0) * c[0] * c[0]); R = c[0] / (c[1] + 1.0); a4 = a6 = a8 = 0.0; sgn = 1.0;
+      /* k1 = (c[1] + 1.0) / ((c[1] - 1.0) * c[0] * c[0]) */ R = c[0] / (c[1] + 1.0); a4 = a6 = a8 = 0.0; sgn = 1.0;
     }
   }
   OPTB_DEV double operator()(double t) const {
@@ -484,7 +489,7 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
   if (ASPH && g == OPTB_G_ASPHERE) {
     // Scan first, solve after: the (expensive) root solve runs once for the whole warp instead of once per
     // sub-interval (lane efficiency 21 -> 31 of 32).
-    const AsphF f(ni[OPTB_NI_AUX], p + 1, ox, oy, oz, dx, dy, dz);
+    const AsphF f(ni[OPTB_NI_AUX], p + 1, nf[OPTB_NF_FOCAL], ox, oy, oz, dx, dy, dz);  // (FOCAL slot of an asphere row: k1, set by the upload)
     const bool asc = (b >= a);
     // All ten sample signs first, as two bit masks: the evaluations are independent, so the fp64 pipe sees ten
     // interleaved dependency chains instead of one (and nothing but 20 bits stays live afterwards).
@@ -823,18 +828,20 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
 }
 
 // np.histogram(x, bins=30, range=(lo, hi)) bin index, -1 outside
-OPTB_DEV int hist_bin(double x, double lo, double hi) {
+// (norm = nb / (hi - lo) and step = (hi - lo) / nb depend on the monitor only: the upload precomputes them)
+OPTB_DEV int hist_bin(double x, double lo, double hi, double norm, double step) {
   const int nb = OPTB_HIST_BINS;
   if (!(x >= lo && x <= hi)) return -1;
-  double norm = nb / (hi - lo);
   int idx = (int)((x - lo) * norm);
   if (idx == nb) idx = nb - 1;
-  double step = (hi - lo) / nb;
   double e0 = fma((double)idx, step, lo);
   double e1 = (idx + 1 == nb) ? hi : fma((double)(idx + 1), step, lo);
   if (x < e0) idx--;
   else if (x >= e1 && idx != nb - 1) idx++;
   return idx;
+}
+OPTB_DEV int hist_bin(double x, double lo, double hi) {
+  return hist_bin(x, lo, hi, OPTB_HIST_BINS / (hi - lo), (hi - lo) / OPTB_HIST_BINS);
 }
 
 }  // namespace optb
