@@ -37,6 +37,9 @@ namespace {
 #ifndef OPTB_BLOCK
 #define OPTB_BLOCK 128
 #endif
+#ifndef OPTB_CULL_FAR
+#define OPTB_CULL_FAR 1   // 0: boxes are only tested the reference's way, never used to dismiss by distance (A/B switch)
+#endif
 #ifndef OPTB_VOTE_SMEM
 #define OPTB_VOTE_SMEM 0   // 1: the walk of shared-memory scenes also re-converges its lanes with a vote before each leaf test
 #endif
@@ -370,6 +373,10 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
     best_t = hs.best_t; best_node = hs.best_node;
     return;
   }
+  // front-to-back dismissal (slab_hit_far): 1 = in the walk and before a parked test; 2 = asphere variants only before a
+  // parked test (their walks stay as they were)
+  constexpr bool kCullWalk = OPTB_CULL_FAR == 1 || (OPTB_CULL_FAR == 2 && !ASPH);
+  constexpr bool kCullPark = OPTB_CULL_FAR != 0;
   unsigned int n_box = 0;
   constexpr int kPark = 4;
   int parked[kPark];
@@ -409,16 +416,24 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
             continue;
           }
           n_box++;
-          if (!slab_hit(br, sv.trav + cand * 8)) continue;  // the child's own lab box (component_group.py:104-107)
+          if (kCullWalk && (*reinterpret_cast<const int*>(sv.trav + cand * 8 + 7) & 2)) {
+            if (slab_hit_far(br, sv.trav + cand * 8, hs.best_t) != 1) continue;
+          } else if (!slab_hit(br, sv.trav + cand * 8)) continue;  // the child's own lab box (component_group.py:104-107)
           leaf = cand;  // (lattice children are leaves without interact caps, never aspheres to park: flatten._grid)
           break;
         }
         if (i >= n) break;
         const double* tv = sv.trav + i * 8;
         const int2 gs = *reinterpret_cast<const int2*>(tv + 6);  // {geometry kind, skip}
-        if (BOXES && *reinterpret_cast<const int*>(tv + 7)) {
-          n_box++;
-          if (!slab_hit(br, tv)) { i = gs.y; continue; }
+        if (BOXES) {
+          const int word = *reinterpret_cast<const int*>(tv + 7);  // bit 0: test the box; bit 1: may dismiss by distance
+          if (word) {
+            n_box++;
+            if (kCullWalk && (word & 2)) {
+              // front to back: a cullable box entered beyond the closest hit so far cannot hold the winner
+              if (slab_hit_far(br, tv, hs.best_t) != 1) { i = gs.y; continue; }
+            } else if (!slab_hit(br, tv)) { i = gs.y; continue; }
+          }
         }
         const int g = gs.x;
         const int cur = i++;
@@ -443,6 +458,9 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
 #pragma unroll
           for (int k = 0; k < kPark; k++) if (k == n_done) leaf = parked[k];
           n_done++;
+          // parked while the closest cheap hit was not known yet: its box may be out of reach by now
+          if (kCullPark && BOXES && (*reinterpret_cast<const int*>(sv.trav + leaf * 8 + 7) & 2) &&
+              slab_hit_far(br, sv.trav + leaf * 8, hs.best_t) == 2) leaf = -1;
         } else {
           searching = false;
         }
@@ -890,6 +908,7 @@ struct optb_scene {
   // recorded on the stream of every trace that reads the blob: releasing the scene waits for this event only,
   // not for the whole device (other streams, NCCL and unrelated kernels keep running)
   cudaEvent_t last_use; bool used;
+  std::vector<unsigned char>* cull;  // cullable bit per node as uploaded (optb_scene_update_nodes keeps it current)
 };
 
 static int fail(optb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -950,6 +969,63 @@ extern "C" int optb_ctx_destroy(optb_ctx* ctx) {
 }
 
 extern "C" const char* optb_last_error(const optb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+// Which boxes may ALSO be used to dismiss a subtree by distance ("cullable"): a hit on a leaf always lies inside the
+// leaf's geometric extent (planar: the aperture in the plane x = 0; curved: the local box that brackets the reference's
+// root search, optical_component.py:197-233), so if the stored lab box contains that extent in the leaf's CURRENT pose,
+// every hit on the leaf is at t >= the box's entry parameter, and a box entered beyond the closest hit found so far
+// cannot change the result. The reference's boxes are cached and may be stale (the flattener ships the
+// object's own `.bbox`): a stale box is still TESTED like the reference does, but never used for dismissal. A group is
+// cullable when its box contains the boxes of all its children, all of them cullable. Capped leaves count every
+// geometric hit, closest or not (optical_component.py:359-362): never cullable, nor is any group above them.
+static void cull_bits(const optb_scene_desc* d, std::vector<unsigned char>& cull) {
+  const int n = d->n_nodes;
+  cull.assign(n, 0);
+  auto contains = [](const double* outer, const double* inner) {
+    for (int ax = 0; ax < 3; ax++) {
+      const double tol = 1e-9 * std::max(1.0, std::max(fabs(inner[2 * ax]), fabs(inner[2 * ax + 1])));
+      if (!(outer[2 * ax] <= inner[2 * ax] + tol && outer[2 * ax + 1] >= inner[2 * ax + 1] - tol)) return false;
+    }
+    return true;
+  };
+  for (int i = n - 1; i >= 0; i--) {  // children before parents (pre-order table, reverse scan)
+    const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
+    const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
+    if (!ni[OPTB_NI_AABB]) continue;
+    const int g = ni[OPTB_NI_GEOM];
+    if (g == OPTB_G_GROUP || g == OPTB_G_GRID) {
+      bool ok = true;
+      for (int j = i + 1; j < ni[OPTB_NI_SKIP] && ok; j = d->node_i[(size_t)j * OPTB_NI_STRIDE + OPTB_NI_SKIP])
+        ok = cull[j] && contains(nf + OPTB_NF_AABB, d->node_f + (size_t)j * OPTB_NF_STRIDE + OPTB_NF_AABB);
+      cull[i] = ok && ni[OPTB_NI_SKIP] > i + 1;
+      continue;
+    }
+    if (ni[OPTB_NI_CAPSLOT] >= 0) continue;
+    const double* p = nf + OPTB_NF_P;
+    double e[6];  // geometric extent of the hittable points in the local frame
+    switch (g) {
+      case OPTB_G_CIRCLE: e[0] = e[1] = 0; e[2] = e[4] = -p[0]; e[3] = e[5] = p[0]; break;
+      case OPTB_G_RECT: e[0] = e[1] = 0; e[2] = -p[0]; e[3] = p[0]; e[4] = -p[1]; e[5] = p[1]; break;
+      case OPTB_G_SPHERE: for (int k = 0; k < 6; k++) e[k] = p[2 + k]; break;
+      case OPTB_G_ASPHERE: e[0] = p[6]; e[1] = p[7]; e[2] = e[4] = -p[0]; e[3] = e[5] = p[0]; break;
+      case OPTB_G_CYL: e[0] = e[2] = -p[0]; e[1] = e[3] = p[0]; e[4] = -p[1] / 2; e[5] = p[1] / 2; break;
+      default: continue;  // polygons, composite apertures: boxes are tested, not used for dismissal
+    }
+    if (!(e[0] <= e[1] && e[2] <= e[3] && e[4] <= e[5])) continue;
+    const double* T = nf + OPTB_NF_T;
+    const double* c = nf + OPTB_NF_ORIGIN;
+    double lab[6] = {INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY};
+    for (int corner = 0; corner < 8; corner++) {
+      const double x = e[corner & 1], y = e[2 + ((corner >> 1) & 1)], z = e[4 + ((corner >> 2) & 1)];
+      for (int ax = 0; ax < 3; ax++) {
+        const double v = T[3 * ax] * x + T[3 * ax + 1] * y + T[3 * ax + 2] * z + c[ax];
+        lab[2 * ax] = std::min(lab[2 * ax], v); lab[2 * ax + 1] = std::max(lab[2 * ax + 1], v);
+      }
+    }
+    // (a curved leaf finds roots up to 1e-9 outside its bracket; the tolerance of `contains` covers that)
+    cull[i] = contains(nf + OPTB_NF_AABB, lab);
+  }
+}
 
 // Device-side extras of an asphere row: k1 of the sign / Newton functor (AsphF) in the FOCAL slot, which a refractive
 // leaf does not use. Same expressions, same IEEE operations as the device used to evaluate per test.
@@ -1041,11 +1117,15 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
       parent[i] = open.empty() ? -1 : open.back();
       if (ni[OPTB_NI_GEOM] == OPTB_G_GROUP || ni[OPTB_NI_GEOM] == OPTB_G_GRID) open.push_back(i);
     }
+    s->cull = new std::vector<unsigned char>();
+    std::vector<unsigned char>& cull = *s->cull;
+    cull_bits(d, cull);
     for (int i = 0; i < d->n_nodes; i++) {  // compact traversal records
       unsigned char* tv = host.data() + s->off.trav + (size_t)i * 64;
       const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
       memcpy(tv, d->node_f + (size_t)i * OPTB_NF_STRIDE + OPTB_NF_AABB, 48);
-      const int32_t pack[4] = {ni[OPTB_NI_GEOM], ni[OPTB_NI_SKIP], ni[OPTB_NI_AABB], parent[i]};
+      // box word: bit 0 = test the box (component_group.py:98-107), bit 1 = the box may dismiss by distance (cull_bits)
+      const int32_t pack[4] = {ni[OPTB_NI_GEOM], ni[OPTB_NI_SKIP], (ni[OPTB_NI_AABB] ? 1 : 0) | (cull[i] ? 2 : 0), parent[i]};
       memcpy(tv + 48, pack, 16);
     }
   }
@@ -1125,6 +1205,17 @@ extern "C" int optb_scene_update_nodes(optb_ctx* ctx, optb_scene* s, const optb_
     CK(cudaMemcpyAsync(s->d_blob + s->off.ni + (size_t)i * OPTB_NI_STRIDE * 4, ni, OPTB_NI_STRIDE * 4, cudaMemcpyHostToDevice, st), "update node_i");
     CK(cudaMemcpyAsync(s->d_blob + s->off.trav + (size_t)i * 64, nf + OPTB_NF_AABB, 48, cudaMemcpyHostToDevice, st), "update box");
   }
+  // a moved node may change which boxes are allowed to dismiss by distance, up to the root: recompute, send the changes
+  if (s->cull) {
+    std::vector<unsigned char> now;
+    cull_bits(d, now);
+    for (int i = 0; i < d->n_nodes; i++) {
+      if (now[i] == (*s->cull)[i]) continue;
+      const int32_t word = (d->node_i[(size_t)i * OPTB_NI_STRIDE + OPTB_NI_AABB] ? 1 : 0) | (now[i] ? 2 : 0);
+      CK(cudaMemcpyAsync(s->d_blob + s->off.trav + (size_t)i * 64 + 56, &word, 4, cudaMemcpyHostToDevice, st), "update box word");
+    }
+    s->cull->swap(now);
+  }
   // scene-wide properties that pick the kernel variant follow the new rows
   int mc = 0, boxes = 0, asph = 0;
   for (int i = 0; i < d->n_nodes; i++) {
@@ -1160,6 +1251,7 @@ extern "C" int optb_scene_destroy(optb_ctx* ctx, optb_scene* s) {
     }
   }
   if (s->last_use) cudaEventDestroy(s->last_use);
+  delete s->cull;
   delete s;
   return 0;
 }

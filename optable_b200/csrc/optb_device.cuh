@@ -118,6 +118,14 @@ struct BoxRay {
   }
 };
 
+// slab_hit plus front-to-back dismissal: 0 = the reference's test fails; 1 = it passes; 2 = it passes, but the ray
+// point at `t_best` (the closest hit found so far) lies in front of the box's near face on some axis by more than a
+// margin, so nothing inside the box can win. Callers only use 2 on boxes the upload marked cullable (optb.cu
+// cull_bits: the box contains everything hittable below it to 1e-9 relative; curved leaves report roots up to 1e-9
+// outside their bracket). The margin is a DISTANCE along the axis (1e-8 max(1, |face|)), not a ray parameter, so a ray
+// almost parallel to the face is never dismissed on that axis. Rays that take the parallel-axis branch get 0 / 1.
+OPTB_DEV int slab_hit_far(const BoxRay& r, const double* __restrict__ bb, double t_best);
+
 // hit flag of solve_ray_bboxes_intersections for one lab box. With no parallel axis:
 // t_near/t_far per axis are picked by the sign of d instead of min/max of the two plane parameters (identical for
 // a well-formed box, bmin <= bmax).
@@ -148,6 +156,26 @@ OPTB_DEV bool slab_hit(const BoxRay& r, const double* __restrict__ bb) {
     }
   }
   return (t2 + 1e-12 >= t1) && (t2 >= 0.0);
+}
+
+OPTB_DEV int slab_hit_far(const BoxRay& r, const double* __restrict__ bb, double t_best) {
+  if (r.any_par) return slab_hit(r, bb) ? 1 : 0;
+  double tn[3], tf[3], face[3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    face[ax] = bb[2 * ax + r.near[ax]];
+    tn[ax] = (face[ax] - r.o[ax]) * r.inv[ax];
+    tf[ax] = (bb[2 * ax + 1 - r.near[ax]] - r.o[ax]) * r.inv[ax];
+  }
+  const double t2 = dmin(dmin(tf[0], tf[1]), tf[2]);
+  const double e = t2 + 1e-12;
+  if (!((t2 >= 0.0) && (e >= tn[0]) && (e >= tn[1]) && (e >= tn[2]))) return 0;
+  if (!(t_best < INFINITY)) return 1;  // nothing found yet: nothing to be beyond
+  bool far = false;
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++)  // (tn - t_best) |d_ax| = distance from the best hit's point to the near face, along ax
+    far |= (tn[ax] - t_best) > 1e-8 * fmax(1.0, fabs(face[ax])) * fabs(r.inv[ax]);
+  return far ? 2 : 1;
 }
 
 // ---- ASphere profile (component_group.py:1065-1107) ----

@@ -27,10 +27,11 @@ def _both(engine, sc, arrs, limit=2000, q_rtol=parity.RTOL, nthreads=8, **kw):
     errs = parity.compare(RH.arrays_from_result(want), RH.arrays_from_result(got), q_rtol=q_rtol, label="scale")
     for c in (1, 2, 4):  # interactions, monitor rows, dropped
         assert int(got["counters"][c]) == int(want["counters"][c]), c
-    # OPTB_C_TESTS is a work counter, not a result: a child ray starts ON the surface it left, so whether that
-    # surface's zero-thickness box is entered at t = +-1 ulp (and the leaf test attempted, then rejected by
-    # t >= 1e-9 either way) depends on the last bit of the child origin. Allow that, nothing more.
-    assert abs(int(got["counters"][3]) - int(want["counters"][3])) <= 0.05 * int(want["counters"][3])
+    # OPTB_C_TESTS is a work counter, not a result. The engine may do LESS work than the reference's loop (a box
+    # entered beyond the closest hit so far dismisses its subtree: DESIGN.md, front-to-back dismissal), never more --
+    # up to the last bit of a child ray's origin: it starts ON the surface it left, so whether that surface's
+    # zero-thickness box is entered at t = +-1 ulp (leaf test attempted, then rejected by t >= 1e-9) is a coin flip.
+    assert int(got["counters"][3]) <= 1.05 * int(want["counters"][3])
     return got, errs
 
 
