@@ -15,6 +15,12 @@
 #define OPTB_CH_REGS 0   // 1: Children slots written through selects (registers) instead of indexed stores (local
                          // memory). Measured on B200 (r2a): no difference on c2/c3/c4; 0 has fewer spills
 #endif
+// bit 0/3: BoxRay skips 1/0 on parallel axes; bit 1: cdiv decides 0/x itself; bit 2: x/inf of planar ROC terms decided
+// up front. Each removes a ~70-instruction special-operand division path from most pops of the benchmark scenes, and
+// each measured slower or equal on B200 (c2 -1..+3 %, c3 +0.4..+4 %, c4 +1.4 %, ripa -2 %): off.
+#ifndef OPTB_DIVSP
+#define OPTB_DIVSP 0
+#endif
 #ifndef OPTB_STAGED_PLANAR
 #define OPTB_STAGED_PLANAR 1  // planar leaves: x row of Tinv first (intersect_planar) instead of a full to_local
 #endif
@@ -112,7 +118,9 @@ struct BoxRay {
     for (int ax = 0; ax < 3; ax++) {
       par[ax] = fabs(d[ax]) <= 1e-8;
       any_par |= par[ax];
-      inv[ax] = 1.0 / d[ax];
+      // (a parallel axis never reads inv; 1/0 would take the division's ~70-instruction special-operand path on
+      // every pop of an axis-aligned beam)
+      inv[ax] = (OPTB_DIVSP & 8) ? 1.0 / (par[ax] ? 1.0 : d[ax]) : ((OPTB_DIVSP & 1) && par[ax]) ? 0.0 : 1.0 / d[ax];
       near[ax] = inv[ax] < 0.0 ? 1 : 0;
     }
   }
@@ -701,10 +709,20 @@ OPTB_DEV double material_n_cached(const SceneView& sv, const IndexCache& c, int 
   return n;
 }
 
+// num / den, bit for bit, with the two special-operand cases the path meets all the time decided up front: 0 / x (the
+// imaginary part of a planar interface's ABCD denominator) and x / inf (curvature terms of a planar surface, ROC = inf).
+// The hardware division handles them in a ~70-instruction out-of-line path; the result is a zero with the XOR of the signs.
+OPTB_DEV double div_special(double num, double den) {
+  const bool zero_num = (num == 0.0) && (den != 0.0) && (fabs(den) < INFINITY);
+  const bool inf_den = (fabs(den) == INFINITY) && (fabs(num) < INFINITY);
+  if (zero_num || inf_den) return copysign(0.0, num) * copysign(1.0, den);
+  return num / den;
+}
+
 // numpy complex128 division (Smith)
 OPTB_DEV void cdiv(double a, double b, double c, double d, double& re, double& im) {
   if (fabs(c) >= fabs(d)) {
-    double r = d / c, den = fma(d, r, c);
+    double r = (OPTB_DIVSP & 2) ? div_special(d, c) : d / c, den = fma(d, r, c);
     double id = 1.0 / den;
     re = fma(b, r, a) * id; im = fma(-a, r, b) * id;
   } else {
@@ -821,11 +839,11 @@ OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, con
   if (hasq) {  // ABCD of the refraction / of the reflection (:648-666); each only when a child will carry it
     double qr = ray.qre + t, qi = ray.qim;
     if (sin_t < 1 && trans > 0) {
-      double Cc = (nin - nout) / (ROC * nout);
+      double Cc = (OPTB_DIVSP & 4) ? div_special(nin - nout, ROC * nout) : (nin - nout) / (ROC * nout);
       cdiv(qr, qi, fma(Cc, qr, ratio), Cc * qi, qtr, qti);
     }
     if (!(sin_t < 1) || want_refl) {
-      double C2 = 2.0 / ROC;
+      double C2 = (OPTB_DIVSP & 4) ? div_special(2.0, ROC) : 2.0 / ROC;
       cdiv(qr, qi, fma(C2, qr, 1.0), C2 * qi, qrr, qri);
     }
   }

@@ -376,6 +376,33 @@ def callable_material(ns):
     return Scene([slab, face, back], rays, [mon], limit={"max_trace_num": 60})
 
 
+def stale_boxes(ns):
+    """`.bbox` caches on first use (optical_component.py:63-67, component_group.py:28-32) and a later move
+    does not refresh it, so ComponentGroup.interact (component_group.py:98-107) tests boxes of where things WERE.
+    `near` sits at x = 5 but its box still says x = 20: the reference finds it (the ray crosses the old box too) IN FRONT
+    of the splitter at x = 10, so its box must not be used to dismiss it by distance. `ghost` was moved into the beam at
+    x = 15 but its box is still at y = 30: the reference never sees it. `lens` moved along the beam with a fresh box."""
+    near = ns.CircleRefractive([20, 0, 0], radius=2.0, n1=1.0, n2=1.5)
+    ghost = ns.Mirror([15, 30, 0], radius=2.0)
+    _ = near.bbox, ghost.bbox
+    near.TX(-15)
+    ghost.TY(-30)
+    split = ns.BeamSplitter([10, 0, 0], width=4, height=4, eta=0.4).RotZ(0.2)
+    back = ns.SphereRefractive([27.0 - 9.0, 0, 0], radius=9.0, height=0.3, n1=1.5, n2=1.0)
+    g = ns.ComponentGroup([0, 0, 0])
+    g.add_components([split, near, ghost, back])
+    _ = g.bbox
+    lens = ns.Doublet([40, 0, 0], CT1=1.359, CT2=0.6, R1=18.405, R2=-13.734, R3=-39.933, n12=ns.Glass_NBK7(),
+                      n23=ns.Glass_NSF5(), diameter=7.5)
+    _ = lens.bbox
+    lens.TX(-6)                      # children moved with it; every cached box (group and children) is stale now
+    mon = ns.Monitor([60, 0, 0], 12, 12)
+    rng = np.random.default_rng(SEED + 10)
+    rays = [ns.Ray([0, y, z], [1, 0.01 * rng.standard_normal(), 0.01 * rng.standard_normal()], wavelength=633e-7, w0=50e-4)
+            for y, z in rng.uniform(-1.2, 1.2, (8, 2))]
+    return Scene([g, lens], rays, [mon], limit={"max_trace_num": 60})
+
+
 REGISTRY = {
     "gaussian_beam": gaussian_beam,
     "glass_slab": glass_slab,
@@ -396,6 +423,7 @@ REGISTRY = {
     "ripa": lambda ns: ripa(ns, n_rays=3, limit=150),
     "ripa2_simplified": ripa2_simplified,
     "callable_material": callable_material,
+    "stale_boxes": stale_boxes,
 }
 # a dozen random scenes are ordinary fixtures too (reference-generated goldens); the fuzz tests add hundreds more
 for _seed in range(12):
