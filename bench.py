@@ -126,6 +126,7 @@ def cpu_arm(flat, n_sample, threads, repeats=1, workload=WORKLOAD):
         dt = time.perf_counter() - t0
         inter = int(out["counters"][1])
         best = dt if best is None else min(best, dt)
+    cpu_arm.counters = np.asarray(out["counters"]).astype(np.int64)  # the reference loop's own work counts on the sample
     return inter / best, inter, best
 
 
@@ -380,6 +381,18 @@ def measure(args, D, engine, name, steps, warmup, e2e_steps, with_cpu, peaks, fp
             out["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": f"first {cpu_rays} rays of the same batch ({cpu_inter} interactions in {cpu_dt:.2f} s), "
                                              f"oracle/optb_oracle.c with {threads} threads"}
+            # the same FP64 bound with the work the REFERENCE's loop does per interaction (every child of a hit group box
+            # is tested: component_group.py:98-115) instead of the tests this engine executed -- front-to-back dismissal
+            # skips tests the formula of SURVEY 8(d) charges for, so the executed-work fraction above is the lower one
+            from optable_b200 import _abi as A
+            c = cpu_arm.counters
+            fp = out["roofline"] if out["roofline"]["bound"] == "fp64" else out.get("roofline_fp64")
+            if fp is not None and int(c[A.C_INTERACTIONS]) > 0:
+                ref_flops = (FLOPS_PLANAR * (c[A.C_TESTS] - c[A.C_TESTS_CURVED]) + FLOPS_CURVED * c[A.C_TESTS_CURVED]
+                             + FLOPS_BOX * c[A.C_BOX_TESTS] + FLOPS_INTERACT * c[A.C_INTERACTIONS]) / float(c[A.C_INTERACTIONS])
+                a_ref = ref_flops * inter / (fp["kernel_ms"] * 1e-3) / 1e12
+                fp["reference_loop"] = {"flops_per_interaction": float(ref_flops), "achieved": a_ref, "frac": a_ref / fp["peak"],
+                                        "counts_from": f"oracle/optb_oracle.c on the first {cpu_rays} rays (the reference's loop, no dismissal)"}
             bind_to_gpu_numa_node(D.local)
     dt.scene.close()
     del dt
@@ -412,7 +425,18 @@ def rooflines(name, n, inter, pops, hits, tests, curved, boxes, row_bytes, bundl
             "peak_source": "measured in this run: optb_measure_fp64_peak (8 independent DFMA chains per thread), SM clock %s MHz while it ran" % fp64_peak.get("sm_mhz"),
             "kernel": "trace_kernel", "kernel_ms": trace_ms, "algorithmic_flops": int(flops),
             "flops_per_interaction": flops / max(inter, 1),
-            "formula": "55*planar_leaf_tests + 200*curved_leaf_tests + 25*box_tests + 180*interactions (SURVEY 8d), counts from this run's device counters"}
+            "formula": "55*planar_leaf_tests + 200*curved_leaf_tests + 25*box_tests + 180*interactions (SURVEY 8d), counts from this run's device "
+                       "counters = tests EXECUTED (tests skipped by front-to-back dismissal are not credited; reference_loop credits them)"}
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one `ncu --set full` capture of this very command
+    # (profiles/r2_traffic.json names the capture); only valid for the batch size it was captured at
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            cap = json.load(f).get(name)
+        if cap and int(cap["rays_per_gpu"]) == int(n):
+            r_hbm["traffic"] = r_fp["traffic"] = int(cap["dram_bytes_per_launch"])
+            r_hbm["traffic_source"] = r_fp["traffic_source"] = cap["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     binding, other = (r_fp, r_hbm) if r_fp["frac"] >= r_hbm["frac"] else (r_hbm, r_fp)
     return {"roofline": binding, "roofline_" + other["bound"]: other}
 
