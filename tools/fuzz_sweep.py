@@ -54,6 +54,12 @@ for seed in range(first, first + count):
 print(f"{count} scenes, {rays} rays, {pops} pops, {hits} monitor rows in {time.time()-t0:.0f} s")
 print("flagged (tie) roots:", len(flagged), flagged[:20])
 print("failures:", len(failures), failures[:5])
+import re
+by_kind = collections.defaultdict(list)   # value-tolerance failures by field; anything else (a count / index mismatch) as "DECISION"
+for seed, msg in failures:
+    m = re.match(r"seed \d+( restarted)?: (\w+) max relative error ([0-9.e+-]+)", msg)
+    by_kind[(m.group(2) + (m.group(1) or "")) if m else "DECISION"].append((float(m.group(3)) if m else 0.0, seed))
+print("failures by kind (count, worst value, its seed):", {k: (len(v), *max(v)) for k, v in by_kind.items()})
 print("worst relative errors:", {k: float(f"{v:.2e}") for k, v in worst.items()})
 print(f"restarted single interactions: {rays1} rays, {pops1} pops, flagged ties {len(flagged1)}")
 print("worst relative errors (restarted, bar 1e-9; q 1e-5 in scenes with FD-curvature aspheres):", {k: float(f"{v:.2e}") for k, v in worst1.items()})
