@@ -69,7 +69,11 @@ enum {
   OPTB_I_MIRROR = 1,   /* BaseMirror.interact_local            :536-570 */
   OPTB_I_REFRACT = 2,  /* BaseRefraciveSurface.interact_local  :617-717 */
   OPTB_I_THINLENS = 3, /* Lens.interact_local                  :930-948 */
-  OPTB_I_ABSORB = 4    /* Block.interact_local                 :501-503 */
+  OPTB_I_ABSORB = 4,   /* Block.interact_local                 :501-503 */
+  OPTB_I_PASS = 5      /* PointObj / Monitor.interact_local    :438-440, monitor.py:174-175: `return [ray]` -- the child is
+                          the popped ray itself (origin NOT moved to the hit point, q and path length untouched), so it
+                          hits the same surface again at the same t until the pop cap: a Monitor listed in
+                          table.components. Degenerate, reproduced as is. */
 };
 
 /* radius-of-curvature source for the ABCD matrices (optical_component.py:631-639) */

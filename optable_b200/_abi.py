@@ -9,7 +9,7 @@ G_GROUP, G_CIRCLE, G_RECT, G_SPHERE, G_ASPHERE, G_CYL, G_POLY2D, G_POLY3D, G_CSG
 (GRID_NOUTER, GRID_NINNER, GRID_NEXT, GRID_R, GRID_C00, GRID_NHAT, GRID_UD, GRID_VD, GRID_RHOA, GRID_RHOB, GRID_CELLS) = (
     0, 1, 2, 3, 4, 7, 10, 13, 16, 17, 18)
 # interaction kinds
-I_NONE, I_MIRROR, I_REFRACT, I_THINLENS, I_ABSORB = range(5)
+I_NONE, I_MIRROR, I_REFRACT, I_THINLENS, I_ABSORB, I_PASS = range(6)
 ROC_INF, ROC_CONST, ROC_ASPHERE_FD = range(3)
 ASPH_PARAMETRIC, ASPH_EXACT_SPH = 1, 2
 

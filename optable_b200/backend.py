@@ -249,7 +249,9 @@ class Engine:
         torch = self.torch
         rs = self._rays_struct(rays_t)
         n = int(rs.n)
-        splitting = scene.flat.max_children > 1 or params.chain_len > 0 or scene.flat.n_capslots > 0 or params.flag_ambiguity or params.reference_roots
+        has_pass = bool((scene.flat.node_i[:, A.NI_INTER] == A.I_PASS).any())   # runs the general (wavefront) variants
+        splitting = (scene.flat.max_children > 1 or params.chain_len > 0 or scene.flat.n_capslots > 0 or params.flag_ambiguity
+                     or params.reference_roots or has_pass)
         live = 0 if not splitting else int(max_live if max_live is not None else max(4 * n, 1024))
         if scene.flat.n_capslots and not params.caps_slack:  # family-serial mode: total FIFO entries over all families
             live = max(live, min(64 * max(n, 16), n * (int(params.max_trace_num) + 2)))

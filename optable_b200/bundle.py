@@ -145,7 +145,8 @@ class DeviceTrace:
         result buffers and the scene blob are read at replay time, so the caller may overwrite the rays in place
         and move components with `scene.update_nodes(flat.refresh(component))` between replays."""
         torch = self.torch
-        if self.flat.max_children > 1 or self.prm.chain_len > 0 or self.flat.n_capslots:
+        has_pass = bool((self.flat.node_i[:, A.NI_INTER] == A.I_PASS).any())   # pass-through leaves run the wavefront variants
+        if self.flat.max_children > 1 or self.prm.chain_len > 0 or self.flat.n_capslots or has_pass:
             raise NotImplementedError("CUDA-graph replay needs a scene whose interactions emit one ray at most (no host round trips)")
         self.run(rays_t, max_live)          # warm-up: workspace and kernel attributes exist before the capture
         torch.cuda.synchronize()

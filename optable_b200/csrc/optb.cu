@@ -478,7 +478,8 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
 // FLAG = diagnostics variant: the ambiguity mask of SURVEY A.9 is evaluated at every pop (optb_flags.cuh).
 // BRENT = params.reference_roots: curved-surface roots from the reference's own brentq iteration (brentq_dev) instead
 // of the closed-form / Newton root.
-template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = false, bool BRENT = false>
+// PASSK = the scene has an OPTB_I_PASS leaf (a Monitor listed as a component): only the general variants carry that body.
+template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = false, bool BRENT = false, bool PASSK = false>
 // Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
 // spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
 // whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
@@ -590,7 +591,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
           double ox, oy, oz, dx, dy, dz;
           to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
           Children<MAXCH> ch;
-          interact<ASPH, MAXCH>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
+          interact<ASPH, MAXCH, PASSK || SERIAL || FLAG || BRENT>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
           for (int k = 0; k < ch.n; k++) {
             if (tail - head >= a.qcap) { atomicOr(&a.counters[OPTB_C_STATUS], (unsigned long long)OPTB_ST_WORK_OVERFLOW); break; }
             Ray c = ray;
@@ -648,7 +649,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
       hit_leaf = ni[OPTB_NI_LEAF];
       double ox, oy, oz, dx, dy, dz;
       to_local(nf + OPTB_NF_ORIGIN, nf + OPTB_NF_TINV, ray, ni[OPTB_NI_ORTHO] != 0, ox, oy, oz, dx, dy, dz);
-      interact<ASPH, MAXCH>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
+      interact<ASPH, MAXCH, PASSK || SERIAL || FLAG || BRENT>(sv, ni, nf, ray, a.unit, ox, oy, oz, dx, dy, dz, t, ch, ic);
       nch = ch.n;
       if (nch == 1 && solo && (!SPLIT || a.chain_len == 0 || chained + 1 < a.chain_len)) {
         // the root's alive set is this one ray: BFS order is trivially kept, continue in registers
@@ -903,7 +904,7 @@ struct optb_ctx {
 struct optb_scene {
   unsigned char* d_blob; size_t blob_cap; uint32_t blob_bytes; SceneOff off;
   int n_nodes, n_leaves, n_mats, n_mons, n_caps; long long n_aux;
-  int max_children; int has_boxes; int has_asph; int has_grid;
+  int max_children; int has_boxes; int has_asph; int has_grid; int has_pass;
   bool in_smem; bool hist_smem; uint32_t smem_bytes;
   // recorded on the stream of every trace that reads the blob: releasing the scene waits for this event only,
   // not for the whole device (other streams, NCCL and unrelated kernels keep running)
@@ -1063,7 +1064,7 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
     }
     if (g == OPTB_G_GROUP || g == OPTB_G_GRID) continue;
     if (ni[OPTB_NI_SKIP] != i + 1) return fail(ctx, -5, "scene: a leaf must skip to the next node");
-    if (ni[OPTB_NI_INTER] < OPTB_I_MIRROR || ni[OPTB_NI_INTER] > OPTB_I_ABSORB) return fail(ctx, -5, "scene: unknown interaction kind");
+    if (ni[OPTB_NI_INTER] < OPTB_I_MIRROR || ni[OPTB_NI_INTER] > OPTB_I_PASS) return fail(ctx, -5, "scene: unknown interaction kind");
     if (ni[OPTB_NI_MAT1] < 0 || ni[OPTB_NI_MAT1] >= d->n_materials || ni[OPTB_NI_MAT2] < 0 || ni[OPTB_NI_MAT2] >= d->n_materials)
       return fail(ctx, -5, "scene: material index out of range");
     if (ni[OPTB_NI_CAPSLOT] >= d->n_capslots) return fail(ctx, -5, "scene: cap slot out of range");
@@ -1149,11 +1150,12 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
     if (ni[OPTB_NI_AABB]) s->has_boxes = 1;
     if (ni[OPTB_NI_GEOM] == OPTB_G_ASPHERE) s->has_asph = 1;
     if (ni[OPTB_NI_GEOM] == OPTB_G_GRID) s->has_grid = 1;
+    if (ni[OPTB_NI_INTER] == OPTB_I_PASS) s->has_pass = 1;
     int k = 0;
     switch (ni[OPTB_NI_INTER]) {
       case OPTB_I_MIRROR: k = (nf[OPTB_NF_REFL] > 0) + (nf[OPTB_NF_TRANS] > 0); break;
       case OPTB_I_REFRACT: k = nf[OPTB_NF_REFL] > 0 ? 2 : 1; break;
-      case OPTB_I_THINLENS: k = 1; break;
+      case OPTB_I_THINLENS: case OPTB_I_PASS: k = 1; break;
       default: k = 0;
     }
     mc = std::max(mc, k);
@@ -1217,22 +1219,23 @@ extern "C" int optb_scene_update_nodes(optb_ctx* ctx, optb_scene* s, const optb_
     s->cull->swap(now);
   }
   // scene-wide properties that pick the kernel variant follow the new rows
-  int mc = 0, boxes = 0, asph = 0;
+  int mc = 0, boxes = 0, asph = 0, pass = 0;
   for (int i = 0; i < d->n_nodes; i++) {
     const int32_t* ni = d->node_i + (size_t)i * OPTB_NI_STRIDE;
     const double* nf = d->node_f + (size_t)i * OPTB_NF_STRIDE;
     if (ni[OPTB_NI_AABB]) boxes = 1;
     if (ni[OPTB_NI_GEOM] == OPTB_G_ASPHERE) asph = 1;
+    if (ni[OPTB_NI_INTER] == OPTB_I_PASS) pass = 1;
     int k = 0;
     switch (ni[OPTB_NI_INTER]) {
       case OPTB_I_MIRROR: k = (nf[OPTB_NF_REFL] > 0) + (nf[OPTB_NF_TRANS] > 0); break;
       case OPTB_I_REFRACT: k = nf[OPTB_NF_REFL] > 0 ? 2 : 1; break;
-      case OPTB_I_THINLENS: k = 1; break;
+      case OPTB_I_THINLENS: case OPTB_I_PASS: k = 1; break;
       default: k = 0;
     }
     mc = std::max(mc, k);
   }
-  s->max_children = mc; s->has_boxes = boxes; s->has_asph = asph;
+  s->max_children = mc; s->has_boxes = boxes; s->has_asph = asph; s->has_pass = pass;
   return 0;
 }
 
@@ -1295,7 +1298,7 @@ RayBuf make_raybuf(unsigned char* base, long long cap) {
   return b;
 }
 bool needs_wavefront(const optb_scene* s, const optb_params* p) {
-  return s->max_children > 1 || p->chain_len > 0 || p->flag_ambiguity || p->reference_roots;  // (the two modes run the SPLIT variants)
+  return s->max_children > 1 || p->chain_len > 0 || p->flag_ambiguity || p->reference_roots || s->has_pass;  // (these run the SPLIT variants)
 }
 // Interact caps make the result depend on the reference's sequential order as soon as two rays of one family can
 // be in flight: splitting scenes, or several initial rays sharing an `_id` (family column given).
@@ -1319,7 +1322,7 @@ SerialLayout serial_layout(long long n_rays, long long n_fam, long long ring_ent
 extern "C" int64_t optb_workspace_bytes(const optb_scene* scene, int64_t n_rays, int64_t max_live) {
   if (!scene || n_rays < 0) return -1;
   // the caller may later pass chain_len > 0, so always size for the wavefront when asked for max_live > 0
-  bool split = scene->max_children > 1 || max_live > 0;
+  bool split = scene->max_children > 1 || max_live > 0 || scene->has_pass;
   int64_t need = (int64_t)ws_layout(n_rays, std::max<int64_t>(max_live, n_rays), split).total;
   if (scene->n_caps > 0)  // family-serial mode: max_live = total FIFO entries over all families
     need = std::max<int64_t>(need, (int64_t)serial_layout(n_rays, n_rays, std::max<int64_t>(max_live, 8 * n_rays)).total);
@@ -1442,6 +1445,10 @@ static int trace_impl(optb_ctx* ctx, const optb_scene* scene, const optb_rays* r
   static const Kern flag_table[2] = {trace_kernel<false, false, 1, true, true, true>, trace_kernel<true, false, 1, true, true, true>};
   Kern kern = serial ? serial_table[scene->in_smem ? 1 : 0]
                      : table[scene->in_smem ? 1 : 0][boxmode][scene->has_asph ? 1 : 0][split ? 1 : 0];
+  // a pass-through leaf (OPTB_I_PASS) only exists in the general variants: this one, or the three kinds below
+  static const Kern pass_table[2] = {trace_kernel<false, false, 1, true, true, false, false, true>,
+                                     trace_kernel<true, false, 1, true, true, false, false, true>};
+  if (scene->has_pass && !serial) kern = pass_table[scene->in_smem ? 1 : 0];
   if (prm->flag_ambiguity) kern = flag_table[scene->in_smem ? 1 : 0];
   // params.reference_roots: the general variants with brentq_dev (parallel and family-serial)
   static const Kern brent_table[2][2] = {{trace_kernel<false, false, 1, true, true, false, true>, trace_kernel<true, false, 1, true, true, false, true>},

@@ -768,28 +768,35 @@ OPTB_DEV void dir_to_lab(const double* __restrict__ T, bool ortho, double lx, do
 }
 
 // interact_local bodies for the winning leaf. (ox..dz) is the ray in the leaf's local frame, t the hit parameter.
-template <bool ASPH, int N>
+template <bool ASPH, int N, bool PASSK>
 OPTB_COLD void interact(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ nf,
                        const Ray& ray, double unit, double ox, double oy, double oz, double dx, double dy, double dz,
                        double t, Children<N>& ch, const IndexCache& ic) {
   const double* T = nf + OPTB_NF_T;
   const double* c = nf + OPTB_NF_ORIGIN;
   const bool ortho = ni[OPTB_NI_ORTHO] != 0;
-  double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+  const int kind = ni[OPTB_NI_INTER];
+  // OPTB_I_PASS (PointObj / Monitor `return [ray]`, optical_component.py:438-440, monitor.py:174-175), PASSK variants
+  // only, rides on the thin lens body: the child is the popped ray itself taken through Tinv and T once (:366-372),
+  // i.e. a thin lens with f = inf and transmission 1 (the flattener writes both) applied at the ray's own ORIGIN
+  // (t = 0 below: fma(0, d, o) is o exactly) that leaves q alone. It is compiled into the general kernel variants only
+  // (trace_impl routes scenes with such a leaf there): in the specialised ones a branch of its own cost c4 +7 %, an
+  // out-of-line body +16 %, this select +2 % -- for a degenerate case no example scene contains.
+  const double tp = (PASSK && kind == OPTB_I_PASS) ? 0.0 : t;
+  double Px = fma(tp, dx, ox), Py = fma(tp, dy, oy), Pz = fma(tp, dz, oz);
   ch.n = 0;
   ch.ox = dot3(T[0], T[1], T[2], Px, Py, Pz) + c[0];
   ch.oy = dot3(T[3], T[4], T[5], Px, Py, Pz) + c[1];
   ch.oz = dot3(T[6], T[7], T[8], Px, Py, Pz) + c[2];
   const bool hasq = (ray.flags & OPTB_RF_HASQ) != 0;
-  const int kind = ni[OPTB_NI_INTER];
   const double refl = nf[OPTB_NF_REFL], trans = nf[OPTB_NF_TRANS];
   ch.pl = fma(t, ray.n, ray.pl);  // Ray.pathlength ray.py:145-147
   if (kind == OPTB_I_ABSORB) return;  // Block :501-503
   double gx, gy, gz;
-  if (kind == OPTB_I_THINLENS) {      // Lens :930-948
+  if (PASSK ? kind >= OPTB_I_THINLENS : kind == OPTB_I_THINLENS) {  // Lens :930-948 (and OPTB_I_PASS, see above)
     double f = nf[OPTB_NF_FOCAL];
     double qre = ray.qre, qim = ray.qim;
-    if (hasq) {
+    if (hasq && (!PASSK || kind == OPTB_I_THINLENS)) {
       double q1r = ray.qre + t, q1i = ray.qim;
       cdiv(q1r, q1i, 1.0 - q1r / f, -(q1i / f), qre, qim);
     }

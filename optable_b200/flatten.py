@@ -469,8 +469,6 @@ class FlatScene:
         sname = type(comp.surface).__name__
         if "PointObj" in names or sname == "Point":
             return None  # Point.f = |P| never changes sign -> never hit (surfaces.py:68-86)
-        if "Monitor" in names:
-            raise FlattenError("a Monitor inside table.components is a pass-through that re-hits itself; unsupported")
         ni, nf = self._blank()
         self._row_owner[id(ni)] = comp
         ni[A.NI_AABB] = 1 if in_group else 0
@@ -577,6 +575,12 @@ class FlatScene:
         elif "Block" in names:
             ni[A.NI_INTER] = A.I_ABSORB
             nchild = 0
+        elif "Monitor" in names:
+            # Monitor.interact_local returns the ray itself (monitor.py:174-175): a monitor listed as a COMPONENT hands
+            # every ray that reaches it back unchanged, to be hit again until the pop cap
+            ni[A.NI_INTER] = A.I_PASS
+            nf[A.NF_FOCAL], nf[A.NF_TRANS] = math.inf, 1.0   # the device runs it as a thin lens of no power at t = 0
+            nchild = 1
         else:
             raise FlattenError(f"component class {type(comp).__name__} has no device interaction")
         self.max_children = max(self.max_children, nchild)

@@ -403,6 +403,22 @@ def stale_boxes(ns):
     return Scene([g, lens], rays, [mon], limit={"max_trace_num": 60})
 
 
+def monitor_as_component(ns):
+    """`Monitor.interact_local` returns `[ray]` (monitor.py:174-175), so a Monitor listed in
+    table.components is a pass-through that hands the popped ray back UNCHANGED -- same origin -- to be hit again at the
+    same distance on every later pop, until the pop cap drops it. Degenerate, but it is what the reference does: rays that
+    reach the screen stall there (25 pops each here), rays that miss it go on to the mirror; the same Monitor object
+    listed in table.monitors records every one of those dead segments."""
+    lens = ns.Lens([4, 0, 0], focal_length=9.0, radius=2.0)
+    screen = ns.Monitor([8, 0.5, 0], 1.2, 1.2).RotZ(0.15)
+    mirror = ns.Mirror([12, 0, 0], radius=3.0).RotZ(2.8)
+    far = ns.Monitor([6, -6, 0], 6, 6).RotZ(-1.2)
+    rng = np.random.default_rng(SEED + 11)
+    rays = [ns.Ray([0, y, z], [1, 0.01 * rng.standard_normal(), 0.01 * rng.standard_normal()], wavelength=633e-7, w0=40e-4)
+            for y, z in rng.uniform(-1.5, 1.5, (10, 2))]
+    return Scene([lens, screen, mirror], rays, [screen, far], limit={"max_trace_num": 25})
+
+
 REGISTRY = {
     "gaussian_beam": gaussian_beam,
     "glass_slab": glass_slab,
@@ -424,6 +440,7 @@ REGISTRY = {
     "ripa2_simplified": ripa2_simplified,
     "callable_material": callable_material,
     "stale_boxes": stale_boxes,
+    "monitor_as_component": monitor_as_component,
 }
 # a dozen random scenes are ordinary fixtures too (reference-generated goldens); the fuzz tests add hundreds more
 for _seed in range(12):
