@@ -37,6 +37,9 @@ namespace {
 #ifndef OPTB_BLOCK
 #define OPTB_BLOCK 128
 #endif
+#ifndef OPTB_BIG_EXTRA
+#define OPTB_BIG_EXTRA 1   // extra resident CTAs per SM for the variants whose scene tables stay in L1/L2
+#endif
 #ifndef OPTB_CULL_FAR
 #define OPTB_CULL_FAR 1   // 0: boxes are only tested the reference's way, never used to dismiss by distance (A/B switch)
 #endif
@@ -489,7 +492,7 @@ template <bool SMEM, bool SERIAL, int BOXES, bool ASPH, bool SPLIT, bool FLAG = 
 // Resident CTAs per SM: scenes staged in shared memory are bound by dependent fp64 chains and lose more to the
 // spills of a tighter register budget than they gain from a fifth CTA (measured 6.32 -> 7.62 ms on c2); scenes
 // whose tables stay in L1/L2 (thousands of leaves) are memory-latency bound and gain from it (ripa 30.6 -> 29.8 ms).
-__global__ void __launch_bounds__(kBlock, kResident((SMEM || ASPH || SERIAL) ? OPTB_MIN_BLOCKS : OPTB_MIN_BLOCKS + 1))
+__global__ void __launch_bounds__(kBlock, kResident((SMEM || ASPH || SERIAL) ? OPTB_MIN_BLOCKS : OPTB_MIN_BLOCKS + OPTB_BIG_EXTRA))
 trace_kernel(const __grid_constant__ TraceArgs a) {
   constexpr int MAXCH = (SPLIT || SERIAL) ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem_raw[];
