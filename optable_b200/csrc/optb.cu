@@ -37,6 +37,9 @@ namespace {
 #ifndef OPTB_BLOCK
 #define OPTB_BLOCK 128
 #endif
+#ifndef OPTB_LANE_REFILL
+#define OPTB_LANE_REFILL 1   // 0: a warp works through one 32-ray chunk at a time in every variant (A/B switch)
+#endif
 #ifndef OPTB_BIG_EXTRA
 #define OPTB_BIG_EXTRA 1   // extra resident CTAs per SM for the variants whose scene tables stay in L1/L2
 #endif
@@ -545,10 +548,16 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
   unsigned int c_pops = 0, c_inter = 0, c_drop = 0, c_hits = 0;  // per thread; widened when reduced
 
   while (true) {
+    constexpr bool PHASE = OPTB_PHASE_SYNC && !SERIAL && !FLAG && BOXES != 0 && !ASPH;
+    // REFILL: a lane whose ray is finished (its chain ended, or it was a one-pop ray) takes the next ray from the work
+    // counter at once instead of idling until the slowest of its warp's 32 rays is done. Chains of a splitting scene end
+    // after very different numbers of pops (ripa generation 0: 23.8 of 32 lanes busy on average). The work counter of
+    // these variants counts rays, not 32-ray chunks.
+    constexpr bool REFILL = OPTB_LANE_REFILL && PHASE && SPLIT;
     unsigned int chunk = 0;
-    if (lane == 0) chunk = atomicAdd(&a.hdr->work_ctr, 1u);
+    if (lane == 0) chunk = atomicAdd(&a.hdr->work_ctr, REFILL ? 32u : 1u);
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    long long i = (long long)chunk * 32 + lane;
+    long long i = (REFILL ? (long long)chunk : (long long)chunk * 32) + lane;
     // PHASE: the warps of a CTA start every pop together (one barrier per pop). The kernel's hot code (35-55 KB) is
     // larger than the 32 KB instruction cache; rays of one launch follow similar paths, so warps that start a pop
     // together run the same stretch of code at the same time and share the cache instead of thrashing it (ncu on the
@@ -556,7 +565,6 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
     // (B200, r2n): scenes with a box walk and no aspheres -- lens groups of spheres (c3 -5 %), large arrays
     // (ripa -6 %); not for bare mirror scenes, whose pops are too short to pay for a barrier (c4 +17 %), nor for
     // asphere scenes (c2 +-0). A warp that ran out of rays keeps meeting the barrier until the whole CTA is done.
-    constexpr bool PHASE = OPTB_PHASE_SYNC && !SERIAL && !FLAG && BOXES != 0 && !ASPH;
     const bool has = i < n_in;
     if (PHASE) { if (!__syncthreads_or(has ? 1 : 0)) break; }
     else {
@@ -621,7 +629,7 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
     Ray ray; bool solo = true; uint32_t gcount = 1, pop_base0 = 0;
     if (has) load_ray(a, i, ray, solo, gcount, pop_base0);
     if (!SPLIT) solo = true;
-    const uint32_t pop_base_next = (!SPLIT || a.gen0) ? 0u : (pop_base0 + gcount);
+    uint32_t pop_base_next = (!SPLIT || a.gen0) ? 0u : (pop_base0 + gcount);
     int nch = 0;
     int chained = 0;
     int hit_leaf = 0;
@@ -670,7 +678,45 @@ trace_kernel(const __grid_constant__ TraceArgs a) {
       }
       return false;
     };
-    if constexpr (PHASE) {
+    // what a finished ray leaves behind: its children in slots 2i / 2i + 1 of the sparse buffer
+    auto store_children = [&]() {
+      a.nchild[i] = (uint8_t)nch;
+      uint32_t pb = solo ? ray.pop + 1u : pop_base_next;
+      if (nch > 0) store_child(a.c, 2 * i, ray, ch.ox, ch.oy, ch.oz, ch.pl, ch.dx[0], ch.dy[0], ch.dz[0], ch.I[0],
+                               ch.qre[0], ch.qim[0], ch.nmed[0], 0, pb, hit_leaf);
+      if (nch > 1) store_child(a.c, 2 * i + 1, ray, ch.ox, ch.oy, ch.oz, ch.pl, ch.dx[MAXCH - 1], ch.dy[MAXCH - 1],
+                               ch.dz[MAXCH - 1], ch.I[MAXCH - 1], ch.qre[MAXCH - 1], ch.qim[MAXCH - 1],
+                               ch.nmed[MAXCH - 1], 1, pb, hit_leaf);
+    };
+    if constexpr (REFILL) {
+      bool active = has;
+      bool more = true;  // (warp-uniform) the work counter has not run past the wavefront yet
+      while (__syncthreads_or(active ? 1 : 0)) {
+        if (active) {
+          active = pop_step();
+          if (!active && a.nchild) store_children();
+        }
+        const unsigned need = more ? __ballot_sync(0xffffffffu, !active) : 0u;
+        if (need) {
+          const int leader = __ffs(need) - 1;
+          unsigned int base = 0;
+          if (lane == leader) base = atomicAdd(&a.hdr->work_ctr, (unsigned int)__popc(need));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if ((long long)base + __popc(need) >= n_in) more = false;
+          if (!active) {
+            i = (long long)base + __popc(need & ((1u << lane) - 1u));
+            if (i < n_in) {
+              if (a.perm) i = a.perm[i];
+              load_ray(a, i, ray, solo, gcount, pop_base0);
+              pop_base_next = a.gen0 ? 0u : (pop_base0 + gcount);
+              nch = 0; chained = 0; hit_leaf = 0; ch.n = 0;
+              active = true;
+            }
+          }
+        }
+      }
+      continue;  // (the next trip finds the counter exhausted and leaves through the barrier above)
+    } else if constexpr (PHASE) {
       bool active = has;
       while (__syncthreads_or(active ? 1 : 0)) {
         if (active) active = pop_step();
