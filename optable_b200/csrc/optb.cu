@@ -53,6 +53,10 @@ namespace {
 #define OPTB_PARK_ALWAYS 0   // 1: every variant parks the radiometric ray state in shared memory during the hit search
                              // (0: only asphere / lattice variants; measured r2u: c4 115.0 -> 110.8 ms, c3 8.00 -> 7.81)
 #endif
+#ifndef OPTB_WIN_BATCH
+#define OPTB_WIN_BATCH 1   // lattice windows of up to 8 x 8 cells: the cells' box tests as one batch, two at a time
+                           // (ripa 21.45 -> 21.19 ms per 1e6 rays; 0 = one candidate at a time, A/B switch)
+#endif
 #ifndef OPTB_PHASE_SYNC
 #define OPTB_PHASE_SYNC 1   // 0: no per-pop CTA barrier in any variant (A/B switch)
 #endif
@@ -399,6 +403,7 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
   const BoxRay br(ray.ox, ray.oy, ray.oz, BOXES ? ray.dx : 1.0, BOXES ? ray.dy : 1.0, BOXES ? ray.dz : 1.0);
   // lattice cursor (BOXES = 2): group being listed (-1: none), cell cursor, window, cursor over the extra children
   int g_node = -1, g_i = 0, g_j = 0, g_i1 = -1, g_j0 = 0, g_j1 = -1, g_x = 0;
+  unsigned long long g_mask = 0ull;  // (OPTB_WIN_BATCH) window cells whose box test passed and that are still to be visited
   const double* gd = nullptr;
   // Warp-synchronous "walk, then test": in every round each lane walks boxes until it holds a leaf (or runs out of
   // nodes and takes a parked asphere), then the lanes that called in together meet again at the vote and run the
@@ -416,6 +421,16 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
         if (BOXES == 2 && g_node >= 0) {
           // next candidate child of the lattice group: window cells in list order, then the off-lattice children
           int cand;
+          if (OPTB_WIN_BATCH && g_mask) {
+            // (batched window: the boxes of all window cells were tested when the window was set up)
+            const int b = __ffsll((long long)g_mask) - 1;
+            g_mask &= g_mask - 1ull;
+            cand = (int)gd[OPTB_GRID_CELLS + (g_i + (b >> 3)) * (int)gd[OPTB_GRID_NINNER] + g_j0 + (b & 7)];
+            if (kCullWalk && (*reinterpret_cast<const int*>(sv.trav + cand * 8 + 7) & 2) && hs.best_t < INFINITY &&
+                slab_far_only(br, sv.trav + cand * 8, hs.best_t)) continue;
+            leaf = cand;
+            break;
+          }
           if (g_i <= g_i1) {
             cand = (int)gd[OPTB_GRID_CELLS + g_i * (int)gd[OPTB_GRID_NINNER] + g_j];
             if (++g_j > g_j1) { g_j = g_j0; g_i++; }
@@ -452,7 +467,37 @@ OPTB_DEV void closest_hit(const TraceArgs& a, const SceneView& sv, const Ray& ra
         if (BOXES == 2 && g == OPTB_G_GRID && !br.any_par) {
           gd = sv.aux + sv.ni[cur * OPTB_NI_STRIDE + OPTB_NI_AUX];
           int i0;
-          if (grid_window(gd, ray, i0, g_i1, g_j0, g_j1)) { g_node = cur; g_i = i0; g_j = g_j0; g_x = 0; }
+          if (grid_window(gd, ray, i0, g_i1, g_j0, g_j1)) {
+            g_node = cur; g_i = i0; g_j = g_j0; g_x = 0;
+            if (OPTB_WIN_BATCH && g_i1 - i0 < 8 && g_j1 - g_j0 < 8 && g_i1 >= i0 && g_j1 >= g_j0) {
+              // The window's box tests as one batch, two at a time: they are independent (each child's own stored box,
+              // component_group.py:104-107), and taken one by one each is a dependent chain of L2 round trips (cell
+              // index -> box -> test -> branch). Bit (row * 8 + column) of g_mask = that cell's box is hit; the walk
+              // then visits the set bits in list order and applies the front-to-back dismissal when it gets to each.
+              const int nin = (int)gd[OPTB_GRID_NINNER];
+              const int total = (g_i1 - i0 + 1) * (g_j1 - g_j0 + 1);
+              int ii = i0, jj = g_j0;
+              unsigned long long m = 0ull;
+#pragma unroll 1
+              for (int c = 0; c < total; c += 2) {
+                int ii2 = ii, jj2 = jj + 1;
+                if (jj2 > g_j1) { jj2 = g_j0; ii2++; }
+                const bool two = c + 1 < total;
+                if (!two) { ii2 = ii; jj2 = jj; }
+                const int ca = (int)gd[OPTB_GRID_CELLS + ii * nin + jj];
+                const int cb = (int)gd[OPTB_GRID_CELLS + ii2 * nin + jj2];
+                const bool ha = slab_hit(br, sv.trav + ca * 8);
+                const bool hb = slab_hit(br, sv.trav + cb * 8);
+                m |= (unsigned long long)(ha ? 1u : 0u) << ((ii - i0) * 8 + (jj - g_j0));
+                m |= (unsigned long long)((hb && two) ? 1u : 0u) << ((ii2 - i0) * 8 + (jj2 - g_j0));
+                jj = jj2 + 1; ii = ii2;
+                if (jj > g_j1) { jj = g_j0; ii++; }
+              }
+              n_box += (unsigned int)total;
+              g_mask = m;
+              g_i1 = i0 - 1;  // the cell cursor below is spent: after the mask come the off-lattice children
+            }
+          }
           continue;  // (no window: fall through into the box hierarchy below this node)
         }
         if (g == OPTB_G_GROUP || g == OPTB_G_GRID) continue;

@@ -186,6 +186,19 @@ OPTB_DEV int slab_hit_far(const BoxRay& r, const double* __restrict__ bb, double
   return far ? 2 : 1;
 }
 
+// The dismissal half of slab_hit_far alone, for a box already known to pass the reference's test and a finite t_best
+// (no parallel axis).
+OPTB_DEV bool slab_far_only(const BoxRay& r, const double* __restrict__ bb, double t_best) {
+  bool far = false;
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    const double face = bb[2 * ax + r.near[ax]];
+    const double tn = (face - r.o[ax]) * r.inv[ax];
+    far |= (tn - t_best) > 1e-8 * fmax(1.0, fabs(face)) * fabs(r.inv[ax]);
+  }
+  return far;
+}
+
 // ---- ASphere profile (component_group.py:1065-1107) ----
 // The reference differentiates this profile numerically (h = 1e-4 radius, surfaces.py:351-369); the second
 // difference amplifies every rounding of f by ~1e8, so the operation order of the Python closure is kept
@@ -331,6 +344,38 @@ struct AsphF {
     else { double d = fma(A * A, s2, -B * B); v = (A >= 0.0) ? d : -d; }
     if (!(s2 >= 0.0)) v = NAN;
     return sgn * v;
+  }
+  // The same decision for the ten scan samples, with the profile form a compile-time constant (with a run-time `form` the
+  // compiler evaluates both forms at every sample and selects), the NaN case (s2 < 0: the reference's f is NaN, neither
+  // positive nor negative) folded into the comparisons, and the sign of R applied to the two masks afterwards instead
+  // of to every value. Bit i of pos / neg: sign(ts_i) > 0 / < 0 -- the masks sign() would give. c2: 5.850 -> 5.804 ms.
+  template <int FORM>
+  OPTB_DEV void scan10(double a, double b, double step, unsigned& pos_out, unsigned& neg_out) const {
+    unsigned pos = 0u, neg = 0u;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      const double t = i == 9 ? b : fma((double)i, step, a);  // np.linspace(a, b, 10)[i], as sample_t
+      const double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
+      const double r2 = fma(Py, Py, Pz * Pz);
+      double A, B, s2;
+      if (FORM == OPTB_ASPH_PARAMETRIC) {
+        s2 = fma(-k1, r2, 1.0);
+        A = fma(r2 * r2, fma(r2, fma(r2, a8, a6), a4), Px) * R;
+        B = r2 + A;
+      } else {
+        s2 = fma(k1, r2, 1.0);
+        A = R; B = Px - R;
+      }
+      double v;
+      if ((A >= 0.0) == (B >= 0.0)) v = A + B;
+      else { double d = fma(A * A, s2, -B * B); v = (A >= 0.0) ? d : -d; }
+      const bool ok = s2 >= 0.0;
+      pos |= ((ok && v > 0.0) ? 1u : 0u) << i;
+      neg |= ((ok && v < 0.0) ? 1u : 0u) << i;
+    }
+    const bool flip = sgn < 0.0;
+    pos_out = flip ? neg : pos;
+    neg_out = flip ? pos : neg;
   }
 };
 
@@ -530,12 +575,8 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
     // All ten sample signs first, as two bit masks: the evaluations are independent, so the fp64 pipe sees ten
     // interleaved dependency chains instead of one (and nothing but 20 bits stays live afterwards).
     unsigned pos = 0u, neg = 0u;
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-      const double v = f.sign(sample_t(i, a, b, step));
-      pos |= (v > 0.0 ? 1u : 0u) << i;
-      neg |= (v < 0.0 ? 1u : 0u) << i;
-    }
+    if (f.form == OPTB_ASPH_PARAMETRIC) f.template scan10<OPTB_ASPH_PARAMETRIC>(a, b, step, pos, neg);
+    else f.template scan10<OPTB_ASPH_EXACT_SPH>(a, b, step, pos, neg);
     unsigned chg = ((pos & (neg >> 1)) | (neg & (pos >> 1))) & 0x1ffu;  // bit i: f(ts_i) * f(ts_i+1) < 0
     double best = -1.0;
     while (chg) {
