@@ -60,8 +60,17 @@ enum {
   OPTB_G_CSG = 8      /* Plane.union / Plane.subtract  surfaces.py:100-136
                          p0 = op (0 = A and not B, 1 = A or B),
                          p1 = kind A, p2,p3 = params A (or aux offset for poly),
-                         p4 = kind B, p5,p6 = params B (or aux offset for poly) */
+                         p4 = kind B, p5,p6 = params B (or aux offset for poly);
+                         p0 = 2: nested composite (an operand is itself a union / subtract): NI_AUX -> postfix
+                         program in the aux pool, [n_tokens, then n_tokens x (code, a, b)]: code = OPTB_G_CIRCLE /
+                         OPTB_G_RECT / OPTB_G_POLY2D pushes that shape's within_boundary (a, b = its params or aux
+                         offset), OPTB_CSG_SUBTRACT / OPTB_CSG_UNION pop B then A and push (A and not B) / (A or B);
+                         at most OPTB_CSG_MAX_DEPTH values on the stack, exactly one left at the end */
 };
+
+#define OPTB_CSG_SUBTRACT (-1)
+#define OPTB_CSG_UNION (-2)
+#define OPTB_CSG_MAX_DEPTH 30
 
 /* interaction kinds: which interact_local body applies (optical_component.py) */
 enum {

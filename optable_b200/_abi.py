@@ -6,6 +6,7 @@ ABI_VERSION = 7
 
 # geometry kinds
 G_GROUP, G_CIRCLE, G_RECT, G_SPHERE, G_ASPHERE, G_CYL, G_POLY2D, G_POLY3D, G_CSG, G_GRID = range(10)
+CSG_SUBTRACT, CSG_UNION, CSG_MAX_DEPTH = -1, -2, 30
 (GRID_NOUTER, GRID_NINNER, GRID_NEXT, GRID_R, GRID_C00, GRID_NHAT, GRID_UD, GRID_VD, GRID_RHOA, GRID_RHOB, GRID_CELLS) = (
     0, 1, 2, 3, 4, 7, 10, 13, 16, 17, 18)
 # interaction kinds

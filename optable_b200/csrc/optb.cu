@@ -1177,7 +1177,27 @@ extern "C" int optb_scene_upload(optb_ctx* ctx, const optb_scene_desc* d, optb_s
     if ((g == OPTB_G_POLY2D || g == OPTB_G_POLY3D) && !poly_ok(ni[OPTB_NI_AUX])) return fail(ctx, -5, "scene: polygon record out of range");
     if (g == OPTB_G_ASPHERE && ni[OPTB_NI_AUX] != OPTB_ASPH_PARAMETRIC && ni[OPTB_NI_AUX] != OPTB_ASPH_EXACT_SPH)
       return fail(ctx, -5, "scene: unknown asphere form");
-    if (g == OPTB_G_CSG) {
+    if (g == OPTB_G_CSG && (int)p[0] == 2) {  // nested composite: a well-formed postfix program in the aux pool
+      const long long off = ni[OPTB_NI_AUX];
+      if (off < 0 || off + 1 > d->n_aux) return fail(ctx, -5, "scene: CSG program out of range");
+      const double nt = d->aux[off];
+      if (!(nt >= 3 && nt <= 4096) || off + 1 + 3 * (long long)nt > d->n_aux) return fail(ctx, -5, "scene: CSG program out of range");
+      int depth = 0;
+      for (int k = 0; k < (int)nt; k++) {
+        const int code = (int)d->aux[off + 1 + 3 * k];
+        if (code == OPTB_G_CIRCLE || code == OPTB_G_RECT || code == OPTB_G_POLY2D) {
+          if (code == OPTB_G_POLY2D && !poly_ok((long long)d->aux[off + 2 + 3 * k])) return fail(ctx, -5, "scene: CSG polygon out of range");
+          if (++depth > OPTB_CSG_MAX_DEPTH) return fail(ctx, -5, "scene: CSG program nests too deep");
+        } else if (code == OPTB_CSG_SUBTRACT || code == OPTB_CSG_UNION) {
+          if (depth < 2) return fail(ctx, -5, "scene: malformed CSG program");
+          depth--;
+        } else {
+          return fail(ctx, -5, "scene: bad CSG token");
+        }
+      }
+      if (depth != 1) return fail(ctx, -5, "scene: malformed CSG program");
+    } else if (g == OPTB_G_CSG) {
+      if ((int)p[0] != 0 && (int)p[0] != 1) return fail(ctx, -5, "scene: bad CSG op");
       for (int q = 0; q < 2; q++) {
         const int k = (int)p[1 + 3 * q];
         if (k != OPTB_G_CIRCLE && k != OPTB_G_RECT && k != OPTB_G_POLY2D) return fail(ctx, -5, "scene: bad CSG operand");

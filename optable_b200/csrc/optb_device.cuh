@@ -254,6 +254,31 @@ OPTB_DEV bool planar_within(const SceneView& sv, int kind, double p0, double p1,
   return false;
 }
 
+// Plane.union / Plane.subtract (surfaces.py:100-136) at a local point: the flat two-operand record, or (p0 = 2) the
+// postfix program of a nested composite; the value stack is a bit stack (depth checked by the upload).
+OPTB_DEV bool csg_within(const SceneView& sv, const int32_t* __restrict__ ni, const double* __restrict__ p,
+                         double Px, double Py, double Pz) {
+  const int op = (int)p[0];
+  if (op != 2) {
+    const bool a = planar_within(sv, (int)p[1], p[2], p[3], Px, Py, Pz);
+    const bool b = planar_within(sv, (int)p[4], p[5], p[6], Px, Py, Pz);
+    return op == 0 ? (a && !b) : (a || b);
+  }
+  const double* prog = sv.aux + ni[OPTB_NI_AUX];
+  const int n = (int)prog[0];
+  unsigned st = 0u;
+  for (int k = 0; k < n; k++) {
+    const int code = (int)prog[1 + 3 * k];
+    if (code > 0) {
+      st = (st << 1) | (planar_within(sv, code, prog[2 + 3 * k], prog[3 + 3 * k], Px, Py, Pz) ? 1u : 0u);
+    } else {
+      const bool b = st & 1u, a = (st >> 1) & 1u;
+      st = ((st >> 2) << 1) | ((code == OPTB_CSG_SUBTRACT ? (a && !b) : (a || b)) ? 1u : 0u);
+    }
+  }
+  return st & 1u;
+}
+
 // surface within_boundary for curved kinds (surfaces.py:230-235, 300-303, 390-393)
 OPTB_DEV bool curved_within(const SceneView& sv, int g, const int32_t* __restrict__ ni, const double* __restrict__ p,
                             double Px, double Py, double Pz) {
@@ -503,9 +528,7 @@ OPTB_DEV double intersect_planar(const SceneView& sv, const int32_t* __restrict_
   const double* p = nf + OPTB_NF_P;
   bool in;
   if (g == OPTB_G_CSG) {
-    bool a = planar_within(sv, (int)p[1], p[2], p[3], Px, Py, Pz);
-    bool b = planar_within(sv, (int)p[4], p[5], p[6], Px, Py, Pz);
-    in = ((int)p[0] == 0) ? (a && !b) : (a || b);
+    in = csg_within(sv, ni, p, Px, Py, Pz);
   } else if (g == OPTB_G_POLY2D) {
     in = poly_within(sv.aux + ni[OPTB_NI_AUX], Px, Py, Pz);
   } else {
@@ -532,9 +555,7 @@ OPTB_DEV double intersect_leaf(const SceneView& sv, const int32_t* __restrict__ 
     double Px = fma(t, dx, ox), Py = fma(t, dy, oy), Pz = fma(t, dz, oz);
     bool in;
     if (g == OPTB_G_CSG) {
-      bool a = planar_within(sv, (int)p[1], p[2], p[3], Px, Py, Pz);
-      bool b = planar_within(sv, (int)p[4], p[5], p[6], Px, Py, Pz);
-      in = ((int)p[0] == 0) ? (a && !b) : (a || b);
+      in = csg_within(sv, ni, p, Px, Py, Pz);
     } else if (g == OPTB_G_POLY2D) {
       in = poly_within(sv.aux + ni[OPTB_NI_AUX], Px, Py, Pz);
     } else {

@@ -125,9 +125,14 @@ OPTB_DEV unsigned flag_pop(const SceneView& sv, const Ray& ray, int best_node, d
       const double Px = fma(tp, dx, ox), Py = fma(tp, dy, oy), Pz = fma(tp, dz, oz);
       bool in;
       if (g == OPTB_G_CSG) {
-        const bool a = planar_within(sv, (int)p[1], p[2], p[3], Px, Py, Pz), b = planar_within(sv, (int)p[4], p[5], p[6], Px, Py, Pz);
-        in = ((int)p[0] == 0) ? (a && !b) : (a || b);
-        edge = planar_edge(sv, (int)p[1], p[2], p[3], Px, Py, Pz, eps) || planar_edge(sv, (int)p[4], p[5], p[6], Px, Py, Pz, eps);
+        in = csg_within(sv, ni, p, Px, Py, Pz);
+        if ((int)p[0] != 2) {
+          edge = planar_edge(sv, (int)p[1], p[2], p[3], Px, Py, Pz, eps) || planar_edge(sv, (int)p[4], p[5], p[6], Px, Py, Pz, eps);
+        } else {  // nested composite: near the edge of any of its shapes
+          const double* prog = sv.aux + ni[OPTB_NI_AUX];
+          for (int k = 0; k < (int)prog[0]; k++)
+            if ((int)prog[1 + 3 * k] > 0) edge = edge || planar_edge(sv, (int)prog[1 + 3 * k], prog[2 + 3 * k], prog[3 + 3 * k], Px, Py, Pz, eps);
+        }
       } else if (g == OPTB_G_POLY2D) {
         in = poly_within(sv.aux + ni[OPTB_NI_AUX], Px, Py, Pz);
         edge = poly_edge_distance(sv.aux + ni[OPTB_NI_AUX], Px, Py, Pz) <= 2e-9;

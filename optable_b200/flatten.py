@@ -510,6 +510,18 @@ class FlatScene:
             return A.G_POLY2D, float(self._poly_record(s)), 0.0
         raise FlattenError(f"surface {n} cannot be used as a planar aperture operand")
 
+    def _csg_program(self, s, prog, depth):
+        """Postfix tokens (code, a, b) of a composite plane; shapes push, operators pop two (include/optb.h)."""
+        if depth > 64:
+            raise FlattenError("composite plane nests too deep")
+        if type(s).__name__ != "Plane":
+            prog.extend(float(v) for v in self._planar_shape(s))
+            return
+        op, sa, sb = _csg_spec(s)
+        self._csg_program(sa, prog, depth + 1)
+        self._csg_program(sb, prog, depth + 1)
+        prog.extend([float(A.CSG_SUBTRACT if op == "subtract" else A.CSG_UNION), 0.0, 0.0])
+
     def _geometry(self, s, sname, ni, nf):
         p = [0.0] * 8
         if sname == "Circle":
@@ -538,9 +550,17 @@ class FlatScene:
         elif sname == "Plane":
             op, sa, sb = _csg_spec(s)
             ni[A.NI_GEOM] = A.G_CSG
-            p[0] = 0.0 if op == "subtract" else 1.0
-            p[1], p[2], p[3] = self._planar_shape(sa)
-            p[4], p[5], p[6] = self._planar_shape(sb)
+            if type(sa).__name__ != "Plane" and type(sb).__name__ != "Plane":
+                p[0] = 0.0 if op == "subtract" else 1.0
+                p[1], p[2], p[3] = self._planar_shape(sa)
+                p[4], p[5], p[6] = self._planar_shape(sb)
+            else:
+                # an operand is itself a union / subtract (surfaces.py:100-136 compose freely): postfix program
+                prog = []
+                self._csg_program(s, prog, 0)
+                p[0] = 2.0
+                ni[A.NI_AUX] = len(self._aux)
+                self._aux.extend([float(len(prog) // 3)] + prog)
         else:
             raise FlattenError(f"unsupported surface class {sname}")
         nf[A.NF_P:A.NF_P + 8] = p

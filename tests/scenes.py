@@ -197,6 +197,28 @@ def extras(ns):
     return Scene([m_union, skew, lens, cyl, tri], rays, [ns.Monitor([12, 0, 0], 8, 8).RotY(0.1)], limit={"max_trace_num": 40})
 
 
+def nested_csg(ns):
+    """Composite apertures whose operands are composites themselves (Plane.union / Plane.subtract compose freely,
+    surfaces.py:100-136): a plate with a keyhole (rectangle minus (circle or slot)), an annulus with a bar ((circle minus
+    circle) or rectangle), and three levels with a polygon; one of them inside a ComponentGroup (merged boxes)."""
+    keyhole = ns.SquareMirror([3, 0, 0], width=1, height=1, reflectivity=0.6, transmission=0.4)
+    keyhole.surface = ns.Rectangle(3.0, 3.0).subtract(ns.Circle(0.5).union(ns.Rectangle(0.3, 2.0)))
+    annulus = ns.SquareRefractive([6, 0, 0], width=1, height=1, n1=1.0, n2=1.5, reflectivity=0.05)
+    annulus.surface = ns.Circle(1.2).subtract(ns.Circle(0.4)).union(ns.Rectangle(3.0, 0.25))
+    deep = ns.SquareMirror([0, 0, 0], width=1, height=1, reflectivity=1.0)
+    tri = ns.Polygon([[-0.6, -0.5], [0.7, -0.4], [0.1, 0.8]])
+    deep.surface = ns.Rectangle(2.0, 1.0).union(ns.Circle(0.9)).subtract(tri).subtract(ns.Circle(0.15).union(ns.Rectangle(0.1, 1.6)))
+    grp = ns.ComponentGroup([10, 0, 0])
+    grp.add_component(deep)
+    grp.RotZ(np.pi + 0.05)
+    rng = np.random.default_rng(SEED + 11)
+    rays = []
+    for _ in range(40):
+        y, z = rng.uniform(-1.6, 1.6, 2)
+        rays.append(ns.Ray([0, y, z], [1, 0.01 * rng.standard_normal(), 0.01 * rng.standard_normal()], wavelength=633e-7, w0=30e-4))
+    return Scene([keyhole, annulus, grp], rays, [ns.Monitor([8, 0, 0], 6, 6), ns.Monitor([-1, 0, 0], 6, 6)], limit={"max_trace_num": 40})
+
+
 def caps_binding(ns):
     """Interact caps that really bind: a TriangularPrism whose faces 2/3 stop interacting after 3 hits
     per ray id, partial reflections everywhere (splitting), and each ray multiplexed into 6 wavelengths that share
@@ -441,6 +463,7 @@ REGISTRY = {
     "callable_material": callable_material,
     "stale_boxes": stale_boxes,
     "monitor_as_component": monitor_as_component,
+    "nested_csg": nested_csg,
 }
 # a dozen random scenes are ordinary fixtures too (reference-generated goldens); the fuzz tests add hundreds more
 for _seed in range(12):

@@ -134,6 +134,30 @@ def test_scene_upload_rejects_malformed_tables():
     engine.upload(flat).close()
 
 
+def test_scene_upload_rejects_malformed_csg_programs():
+    """Nested composite apertures travel as postfix programs in the aux pool (include/optb.h OPTB_G_CSG, p0 = 2): the
+    upload checks that a program is well formed before a kernel ever evaluates it on its bit stack."""
+    from optable_b200 import _abi as A
+    from optable_b200.backend import BackendError, Engine
+
+    engine = Engine.get(0)
+    flat, _, _, _ = golden_io.load("nested_csg")
+    leaves = np.nonzero((flat.node_i[:, A.NI_GEOM] == A.G_CSG) & (flat.node_f[:, A.NF_P] == 2.0))[0]
+    assert len(leaves) == 3
+    off = int(flat.node_i[leaves[0], A.NI_AUX])
+    n_tok = int(flat.aux[off])
+    assert n_tok == 5 and int(flat.aux[off + 1 + 3 * (n_tok - 1)]) == A.CSG_SUBTRACT   # rect circle rect union subtract
+    for where, val in ((off, 4.0),                      # one token short: two values left on the stack
+                       (off + 1 + 3 * 2, float(A.CSG_UNION)),   # operator where the third shape was: stack underflow later
+                       (off + 1, 99.0),                 # unknown token
+                       (off, 1e9)):                     # program runs past the aux pool
+        bad, _, _, _ = golden_io.load("nested_csg")
+        bad.aux[where] = val
+        with pytest.raises(BackendError):
+            engine.upload(bad)
+    engine.upload(flat).close()
+
+
 def test_edge_cases_empty_inputs_and_long_chains():
     """Empty ray list, empty table, one ray bouncing 1e5 times in a closed cavity (the ripa example's pop budget)."""
     table = ob.OpticalTable()
