@@ -493,6 +493,7 @@ OPTB_DEV double sample_t(int i, double a, double b, double step) {
 }
 
 // (one shift and one AND instead of four compares: it runs once or twice per leaf test)
+// (measured: c3 6.64 -> 6.58 ms, c4 110.7 -> 109.8 ms)
 OPTB_DEV bool is_planar_kind(int g) {
   constexpr unsigned kPlanar = (1u << OPTB_G_CIRCLE) | (1u << OPTB_G_RECT) | (1u << OPTB_G_POLY2D) | (1u << OPTB_G_CSG);
   return (kPlanar >> g) & 1u;
