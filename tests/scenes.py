@@ -219,6 +219,45 @@ def nested_csg(ns):
     return Scene([keyhole, annulus, grp], rays, [ns.Monitor([8, 0, 0], 6, 6), ns.Monitor([-1, 0, 0], 6, 6)], limit={"max_trace_num": 40})
 
 
+def random_csg(ns, seed, depth=4, n_rays=48):
+    """One absorbing/reflecting/refracting plate per scene whose aperture is a random composite of circles, rectangles
+    and planar polygons, nested up to `depth` levels of Plane.union / Plane.subtract (surfaces.py:100-136), hit by a
+    grid-like bundle; a monitor behind it records what gets through."""
+    rng = np.random.default_rng(SEED + 5000 + seed)
+
+    def shape(d):
+        if d == 0 or rng.random() < 0.25:
+            k = rng.integers(3)
+            if k == 0:
+                return ns.Circle(float(rng.uniform(0.2, 1.4)))
+            if k == 1:
+                return ns.Rectangle(float(rng.uniform(0.2, 2.6)), float(rng.uniform(0.2, 2.6)))
+            c = rng.uniform(-0.6, 0.6, 2)
+            ang = np.sort(rng.uniform(0, 2 * np.pi, 3 + int(rng.integers(3))))
+            rad = rng.uniform(0.3, 1.2, len(ang))
+            return ns.Polygon([[float(c[0] + r * np.cos(a)), float(c[1] + r * np.sin(a))] for r, a in zip(rad, ang)])
+        a, b = shape(d - 1), shape(d - 1)
+        return a.union(b) if rng.random() < 0.5 else a.subtract(b)
+
+    kind = int(rng.integers(3))
+    if kind == 0:
+        plate = ns.SquareMirror([4, 0, 0], width=1, height=1, reflectivity=0.5, transmission=0.5)
+    elif kind == 1:
+        plate = ns.SquareRefractive([4, 0, 0], width=1, height=1, n1=1.0, n2=1.5, reflectivity=0.1)
+    else:
+        plate = ns.Block([4, 0, 0], width=1, height=1)
+    top = shape(depth)
+    while type(top).__name__ != "Plane":   # at least one operator at the top
+        top = top.union(shape(depth - 1)) if rng.random() < 0.5 else top.subtract(shape(depth - 1))
+    plate.surface = top
+    plate.RotZ(float(rng.uniform(-0.2, 0.2))).RotY(float(rng.uniform(-0.2, 0.2)))
+    rays = []
+    for _ in range(n_rays):
+        y, z = rng.uniform(-1.5, 1.5, 2)
+        rays.append(ns.Ray([0, y, z], [1, 0.02 * rng.standard_normal(), 0.02 * rng.standard_normal()], wavelength=633e-7, w0=30e-4))
+    return Scene([plate], rays, [ns.Monitor([7, 0, 0], 8, 8), ns.Monitor([-1, 0, 0], 8, 8)], limit={"max_trace_num": 20})
+
+
 def caps_binding(ns):
     """Interact caps that really bind: a TriangularPrism whose faces 2/3 stop interacting after 3 hits
     per ray id, partial reflections everywhere (splitting), and each ray multiplexed into 6 wavelengths that share

@@ -157,3 +157,33 @@ def test_fuzz_scenes_with_binding_interact_caps(engine):
             capmax = flat.node_f[flat.node_i[:, 6] >= 0, 39]
             reached += int((raw["cap_counts"].max(axis=1) >= capmax).any())
     assert reached > 20 and flagged <= 3
+
+
+def test_random_nested_composite_apertures(engine):
+    """120 random composites of circles, rectangles and polygons nested up to four operator levels
+    (tests/scenes.random_csg; the CPU suite pins the oracle to the live reference on the first 40): the device's bit-stack
+    evaluation of the flattener's postfix programs against the oracle, strict bars (one interaction deep, nothing to
+    amplify), also with the ambiguity mask on (its own copy of the aperture test)."""
+    import optable_b200 as ob
+    from optable_b200 import _abi as A
+    from optable_b200.flatten import pack_rays, trace_cap
+    from oracle import oracle as O
+    from oracle import ref_harness as RH
+    from tests import scenes
+
+    nested = rows = 0
+    for seed in range(120):
+        sc = scenes.random_csg(ob, seed)
+        flat = sc.flat()
+        nested += int(((flat.node_i[:, A.NI_GEOM] == A.G_CSG) & (flat.node_f[:, A.NF_P] == 2.0)).sum())
+        arrs, fam_ids, unit = pack_rays(sc.rays)
+        params = dict(max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
+        want = RH.arrays_from_result(O.trace(flat, arrs, **params))
+        _, got = _gpu(engine, flat, arrs, params)
+        _, ties = parity.compare_flagging_ties(flat, want, got, rtol=parity.RTOL, q_rtol=parity.RTOL, label=f"random_csg seed {seed}")
+        assert not ties, (seed, ties)
+        if seed % 4 == 0:
+            _, got_f = _gpu(engine, flat, arrs, params, flag_ambiguity=True)
+            parity.compare(want, got_f, label=f"random_csg seed {seed} (flag variant)")
+        rows += len(want["hit_root"])
+    assert nested >= 90 and rows > 1000

@@ -44,6 +44,25 @@ def test_fuzz_scenes_oracle_equals_reference(block):
     assert flagged <= max(1, 2e-3 * rays)
 
 
+def test_random_nested_composite_apertures():
+    """40 random composites of circles, rectangles and polygons, up to four operator levels deep
+    (tests/scenes.random_csg): the postfix programs of the flattener evaluated by the C restatement against the live
+    reference's nested closures (surfaces.py:100-136), ray by ray."""
+    from optable_b200 import _abi as A
+
+    ref = RH.load_reference()
+    nested = 0
+    for seed in range(40):
+        sc = scenes.random_csg(ref, seed)
+        flat = sc.flat()
+        nested += int(((flat.node_i[:, A.NI_GEOM] == A.G_CSG) & (flat.node_f[:, A.NF_P] == 2.0)).sum())
+        arrs, fam_ids, unit = pack_rays(sc.rays)
+        want = RH.run_reference(sc)
+        got = O.trace(flat, arrs, max_trace_num=trace_cap(sc.limit), unit=unit, n_families=len(fam_ids))
+        parity.compare(want, RH.arrays_from_result(got), label=f"random_csg seed {seed}")
+    assert nested >= 30   # (a few draws end up with two simple operands: the flat record)
+
+
 def test_fuzz_scenes_with_binding_interact_caps():
     """Random scenes in which a third of the leaves carry max_interact_count 1-3 and rays come in three-wavelength
     families sharing one id (tests/scenes.fuzz(caps=True)): the visible set depends on the reference's sequential
