@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OPTB_ABI_VERSION 7
+#define OPTB_ABI_VERSION 8  /* 8: OPTB_G_CSG rows may carry a postfix program (p0 = 2) for nested composites */
 
 /* ---- scene node table ------------------------------------------------------
  * The component tree (OpticalTable.components, groups nested to any depth) is

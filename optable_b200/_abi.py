@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes and constants against the compiled library."""
 import ctypes as C
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # geometry kinds
 G_GROUP, G_CIRCLE, G_RECT, G_SPHERE, G_ASPHERE, G_CYL, G_POLY2D, G_POLY3D, G_CSG, G_GRID = range(10)

@@ -21,8 +21,9 @@ _lib = None
 
 def build(force=False):
     """Compile the checker with the committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "optb_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "optb_oracle.c"), os.path.join(_HERE, "Makefile"),
+            os.path.join(os.path.dirname(_HERE), "include", "optb.h")]   # (the header carries the ABI version both sides check)
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
     return _SO
 
